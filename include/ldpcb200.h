@@ -1,0 +1,143 @@
+/*
+ * ldpcb200.h -- C ABI of libldpcb200.so, the B200-native belief-propagation decoder that
+ * stands behind LDPCDecoders.jl's BeliefPropagationDecoder / decode! / batchdecode!.
+ *
+ * The reference has no FFI layer (it is pure Julia); the entry points below are what a
+ * Julia `ccall` shim for this path binds.  Each one cites the reference interface it
+ * replaces (paths relative to /root/reference/).  INTEGRATION.md shows the Julia-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a nonzero LDPCB200_E* code otherwise; nothing
+ *     throws or aborts; ldpcb200_last_error() gives a thread-local message.
+ *   - the caller owns every host buffer for the duration of the call (Julia: GC.@preserve);
+ *     the library owns all device memory, streams and events inside the handle.
+ *   - one in-flight call per handle (the reference decoder is non-reentrant too: shared
+ *     scratch, src/decoders/belief_propagation.jl:125); different handles are independent.
+ *   - there is NO CPU fallback: without a usable CUDA device ldpcb200_create fails.
+ */
+#ifndef LDPCB200_H
+#define LDPCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldpcb200 ldpcb200_t;
+
+/* error codes */
+#define LDPCB200_OK            0
+#define LDPCB200_EINVAL        1   /* bad argument (shape, format, null pointer, unsorted CSC ...) */
+#define LDPCB200_ECUDA         2   /* CUDA runtime error, see ldpcb200_last_error() */
+#define LDPCB200_ENODEVICE     3   /* no CUDA device / requested device missing */
+#define LDPCB200_EUNSUPPORTED  4   /* e.g. node degree above LDPCB200_MAX_DEGREE */
+#define LDPCB200_ENOMEM        5
+
+#define LDPCB200_MAX_DEGREE  128   /* largest check / variable degree the kernels accept */
+
+/* element formats of host matrices at the boundary (column = one syndrome / one error vector,
+ * exactly the shapes batchdecode! takes: belief_propagation.jl:220, test_bp_decoder.jl:24-26) */
+#define LDPCB200_FMT_U8       0   /* column-major bytes 0/1: Matrix{Bool}, Matrix{UInt8}; ld in elements */
+#define LDPCB200_FMT_I64      1   /* column-major int64 0/1: Matrix{Int} (test_bp_decoder.jl:24) */
+#define LDPCB200_FMT_BITS     2   /* Julia BitMatrix chunks: bit (c*rows + r) of a little-endian bit stream; ld ignored */
+#define LDPCB200_FMT_PACKED32 3   /* native: one row of ceil(rows/32) uint32 per column, bit r%32 of word r/32; ld ignored */
+#define LDPCB200_FMT_F64      4   /* column-major Float64 0.0/1.0 (scratch.err, belief_propagation.jl:17,187); outputs only */
+
+/* kernel variants */
+#define LDPCB200_VARIANT_EXACT  0 /* FP64 likelihood-ratio sum-product, op-for-op with belief_propagation.jl:135-178 */
+
+/* kernel families (ldpcb200_info_t.family, option "family") */
+#define LDPCB200_FAMILY_AUTO   0
+#define LDPCB200_FAMILY_SMEM   1  /* persistent, messages resident in shared memory, lane = syndrome */
+#define LDPCB200_FAMILY_GLOBAL 2  /* messages in HBM/L2, edge-major x syndrome-minor slabs */
+
+typedef struct {
+    int64_t s, n, E;            /* checks, variables, edges (nnz of H) */
+    int32_t max_check_degree, max_var_degree;
+    int32_t family;             /* LDPCB200_FAMILY_* actually selected */
+    int32_t ndev;               /* devices the batch is sharded over */
+    int32_t sm_count;           /* SMs of device 0 */
+    int32_t ctas_per_sm;        /* family SMEM: resident CTAs per SM */
+    int32_t threads_per_cta;
+    int32_t smem_bytes;         /* dynamic shared memory per CTA (family SMEM) */
+    int32_t slots;              /* family GLOBAL: resident syndrome slots per device */
+    int32_t syn_words, err_words; /* uint32 words per packed syndrome / error row */
+    int64_t message_bytes;      /* device bytes of the message store per device */
+} ldpcb200_info_t;
+
+/* counters[] layout of the decode calls (summed over all devices of the handle) */
+#define LDPCB200_CTR_DECODED     0  /* syndromes decoded */
+#define LDPCB200_CTR_CONVERGED   1  /* of which converged */
+#define LDPCB200_CTR_ITERATIONS  2  /* sum of executed BP iterations */
+#define LDPCB200_CTR_RESERVED    3
+#define LDPCB200_NUM_COUNTERS    4
+
+const char *ldpcb200_last_error(void);
+int ldpcb200_version(void);
+int ldpcb200_device_count(int32_t *out);
+
+/* Replaces the constructor BeliefPropagationDecoder(H, per, max_iters)
+ * (src/decoders/belief_propagation.jl:61-67): takes sparse_H's CSC arrays
+ * (colptr n+1, rowval E, row indices ascending inside a column -- the SparseMatrixCSC invariant)
+ * and builds the device-resident Tanner graph once.  index_base = 1 for Julia arrays, 0 for C.
+ * devices/ndev: shard set (NULL/0 -> device 0).  Messages need no reset between calls
+ * (reset!, belief_propagation.jl:83-91, becomes a no-op). */
+int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                    int32_t index_base, double per, int32_t max_iters, int32_t variant,
+                    const int32_t *devices, int32_t ndev, ldpcb200_t **out);
+int ldpcb200_destroy(ldpcb200_t *h);
+int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
+
+/* Tunables, set before the first decode (all optional):
+ *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA, family SMEM), "slots" (family GLOBAL),
+ *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
+ *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk). */
+int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);
+
+/* Replaces batchdecode!(decoder, syndromes, errors, success)
+ * (src/decoders/belief_propagation.jl:220-231; 3-argument form abstract_decoder.jl:44-48) and,
+ * with B = 1, decode!(decoder, syndrome) (belief_propagation.jl:121-188).
+ *   syndromes : s x B host matrix in syn_fmt (syn_ld = leading dimension in elements for U8/I64)
+ *   errors    : n x B host matrix in err_fmt, overwritten (errors[:, i] .= guess, :227)
+ *   converged : B bytes (Julia Vector{Bool}), overwritten (success[i] = conv, :226)
+ *   iters     : nullable, B int32 -- executed iterations per syndrome
+ *   posterior_ratio : nullable, n x B column-major doubles R_j = P(e_j=1)/P(e_j=0) after the
+ *               last executed iteration; scratch.log_probabs[j] = log(1/R_j) (belief_propagation.jl:163),
+ *               which is what BeliefPropagationOSDDecoder reads (belief_propagation_osd.jl:52)
+ *   counters  : nullable, LDPCB200_NUM_COUNTERS int64
+ * Blocks until all outputs are in host memory. */
+int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B,
+                          const void *syndromes, int32_t syn_fmt, int64_t syn_ld,
+                          void *errors, int32_t err_fmt, int64_t err_ld,
+                          uint8_t *converged, int32_t *iters, double *posterior_ratio,
+                          int64_t *counters);
+
+/* Same decode with inputs/outputs already resident on one device of the handle, native packed
+ * format (LDPCB200_FMT_PACKED32).  Asynchronous on `stream` (a cudaStream_t; NULL = the handle's
+ * own stream).  d_counters: nullable device pointer to LDPCB200_NUM_COUNTERS uint64 that the
+ * kernels ADD to.  Used by the device-resident benchmark and by sample->decode->score loops. */
+int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
+                           const uint32_t *d_syn_words, uint32_t *d_err_words,
+                           uint8_t *d_converged, int32_t *d_iters, double *d_posterior_ratio,
+                           unsigned long long *d_counters, void *stream);
+
+/* Harness helpers (pattern of test/test_bp_decoder.jl:19-30 moved on-device).
+ * sample: i.i.d. Bernoulli(per) errors from Philox4x32-10 keyed by the global syndrome index
+ * (first .. first+B-1) and their syndromes H*e mod 2, both in packed rows.
+ * score : counts rows where decoded == true error (out[0]) and rows whose decoded error
+ * reproduces the syndrome (out[1]); ADDS into d_out[2] (uint64). */
+int ldpcb200_sample_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, int64_t first,
+                           uint64_t seed, double per,
+                           uint32_t *d_true_err_words, uint32_t *d_syn_words, void *stream);
+int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
+                          const uint32_t *d_true_err_words, const uint32_t *d_err_words,
+                          const uint32_t *d_syn_words, unsigned long long *d_out, void *stream);
+
+/* Number of kernels of this library launched through the handle so far (bench bookkeeping). */
+int ldpcb200_launch_count(const ldpcb200_t *h, int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPCB200_H */

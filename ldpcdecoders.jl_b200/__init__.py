@@ -1,0 +1,12 @@
+"""ldpcb200 -- B200-native belief-propagation decoder behind the LDPCDecoders.jl BP API.
+
+Only the hot path of /root/reference/src/decoders/belief_propagation.jl is implemented:
+csrc/ holds the CUDA kernels and the C ABI (include/ldpcb200.h); decoder.py mirrors the
+reference's decoder interface on top of that ABI; codes.py builds the benchmark matrices.
+"""
+from . import _lib, codes                                              # noqa: F401
+from .decoder import (BeliefPropagationDecoder, BeliefPropagationScratchSpace,   # noqa: F401
+                      decode_b, batchdecode_b, reset_b)
+
+__all__ = ["BeliefPropagationDecoder", "BeliefPropagationScratchSpace", "decode_b", "batchdecode_b",
+           "reset_b", "codes"]

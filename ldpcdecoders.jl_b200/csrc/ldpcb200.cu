@@ -1,0 +1,735 @@
+// ldpcb200.cu -- host side of libldpcb200.so: Tanner-graph builder, device contexts, kernel
+// dispatch and the C ABI declared in include/ldpcb200.h.
+//
+// Path replaced: BeliefPropagationDecoder / decode! / batchdecode! of
+// /root/reference/src/decoders/belief_propagation.jl:38-67,121-188,220-231.
+// No CPU fallback exists in this file: every decode runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ldpcb200.h"
+#include "bp_global.cuh"
+#include "bp_math.cuh"
+#include "bp_smem.cuh"
+#include "formats.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? LDPCB200_ENOMEM : LDPCB200_ECUDA,        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CU(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+struct DeviceCtx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0, smem_per_sm = 0;
+    cudaStream_t stream = nullptr;
+    // graph tables
+    int *d_rowptr = nullptr, *d_colptr = nullptr, *d_ve_slot = nullptr, *d_ve_chk = nullptr;
+    unsigned char *d_tables = nullptr;
+    // family GLOBAL state
+    DevBuf msg, syn, resid, errb, sid, iter, flags, nnz;
+    unsigned long long *d_queue = nullptr;
+    unsigned long long *h_queue = nullptr;    // pinned
+    int nslab_alloc = 0;
+    // host-batch staging
+    DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio, counters, scratch;
+};
+
+}  // namespace
+
+struct ldpcb200 {
+    int64_t s = 0, n = 0, E = 0;
+    double per = 0, p0 = 0;
+    int max_iters = 0, variant = 0;
+    int max_cdeg = 0, max_vdeg = 0;
+    bool big = false;
+    int SW = 0, NW = 0;
+    std::vector<int> rowptr, colptr, ve_slot, ve_chk;
+    std::vector<unsigned char> tables;   // SMEM-family blob
+    int off_colptr = 0, off_ve = 0;
+    // options
+    int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
+    int64_t opt_chunk = 0;
+    // resolved configuration
+    bool configured = false;
+    int family = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0;
+    bp::SmemParams sp_proto{};
+    std::vector<DeviceCtx> dev;
+    std::atomic<long long> launches{0};
+};
+
+namespace {
+
+inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// shared-memory carve-up of family SMEM; returns total bytes
+int smem_layout(const ldpcb200 *h, bp::SmemParams &p)
+{
+    int off = static_cast<int>(h->E) * 32 * 8;
+    p.off_syn = off;    off += h->SW * 128;
+    p.off_resid = off;  off += h->SW * 128;
+    p.off_errb = off;   off += h->NW * 128;
+    p.off_stage = off;  off += h->SW * 128;
+    p.off_nnz = off;    off += 2 * 32 * 4;
+    off = align_up(off, 16);
+    p.off_tables = off; off += static_cast<int>(h->tables.size());
+    off = align_up(off, 8);
+    p.off_mbar = off;   off += 8;
+    return align_up(off, 16);
+}
+
+int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int base)
+{
+    const int64_t s = h->s, n = h->n;
+    if (colptr[0] - base != 0) return fail(LDPCB200_EINVAL, "colptr[0] must equal index_base");
+    const int64_t E = colptr[n] - base;
+    if (E < 0 || E > 0x7fffffff / 64) return fail(LDPCB200_EINVAL, "edge count %lld out of range", (long long)E);
+    h->E = E;
+    h->colptr.assign(n + 1, 0);
+    h->rowptr.assign(s + 1, 0);
+    h->ve_slot.assign(std::max<int64_t>(E, 1), 0);
+    h->ve_chk.assign(std::max<int64_t>(E, 1), 0);
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t a = colptr[j] - base, b = colptr[j + 1] - base;
+        if (b < a || b > E) return fail(LDPCB200_EINVAL, "colptr not monotone at column %lld", (long long)j);
+        h->colptr[j + 1] = static_cast<int>(b);
+        h->max_vdeg = std::max<int>(h->max_vdeg, static_cast<int>(b - a));
+        for (int64_t e = a; e < b; ++e) {
+            const int64_t r = rowval[e] - base;
+            if (r < 0 || r >= s) return fail(LDPCB200_EINVAL, "row index out of range at entry %lld", (long long)e);
+            if (e > a && rowval[e] <= rowval[e - 1])
+                return fail(LDPCB200_EINVAL, "row indices must be strictly ascending inside column %lld", (long long)j);
+            h->ve_chk[e] = static_cast<int>(r);
+            h->rowptr[r + 1]++;
+        }
+    }
+    for (int64_t i = 0; i < s; ++i) {
+        h->max_cdeg = std::max(h->max_cdeg, h->rowptr[i + 1]);
+        h->rowptr[i + 1] += h->rowptr[i];
+    }
+    // check-major edge slots: visiting columns in ascending order makes the variables of every
+    // check ascending, the order nzrange(sparse_HT, i) walks (belief_propagation.jl:137)
+    std::vector<int> fill(h->rowptr.begin(), h->rowptr.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+        for (int e = h->colptr[j]; e < h->colptr[j + 1]; ++e) h->ve_slot[e] = fill[h->ve_chk[e]]++;
+    if (h->max_cdeg > LDPCB200_MAX_DEGREE || h->max_vdeg > LDPCB200_MAX_DEGREE)
+        return fail(LDPCB200_EUNSUPPORTED, "node degree %d exceeds LDPCB200_MAX_DEGREE=%d",
+                    std::max(h->max_cdeg, h->max_vdeg), LDPCB200_MAX_DEGREE);
+    h->big = std::max(h->max_cdeg, h->max_vdeg) > bp::kMaxRegDegree;
+    h->SW = static_cast<int>((s + 31) / 32);
+    h->NW = static_cast<int>((n + 31) / 32);
+    if (h->SW == 0) h->SW = 1;
+    if (h->NW == 0) h->NW = 1;
+    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve u32[E] (slot | chk << 16)
+    if (E <= 0xffff && s <= 0xffff && n <= 0xffff) {
+        const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
+        const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
+        const int total = align_up(o_ve + static_cast<int>(4 * E), 16);
+        h->tables.assign(std::max(total, 16), 0);
+        uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
+        uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
+        uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
+        for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->rowptr[i]);
+        for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->colptr[j]);
+        for (int64_t e = 0; e < E; ++e)
+            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) | (static_cast<uint32_t>(h->ve_chk[e]) << 16);
+        h->off_colptr = o_col;
+        h->off_ve = o_ve;
+    }
+    return 0;
+}
+
+int init_device(ldpcb200 *h, DeviceCtx &d)
+{
+    CU(cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, d.device));
+    if (prop.major < 10)
+        return fail(LDPCB200_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", d.device,
+                    prop.major, prop.minor);
+    d.sm_count = prop.multiProcessorCount;
+    d.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    d.smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    auto up = [&](int **dst, const std::vector<int> &v) -> int {
+        CU(cudaMalloc(dst, sizeof(int) * v.size()));
+        CU(cudaMemcpy(*dst, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int rc;
+    if ((rc = up(&d.d_rowptr, h->rowptr))) return rc;
+    if ((rc = up(&d.d_colptr, h->colptr))) return rc;
+    if ((rc = up(&d.d_ve_slot, h->ve_slot))) return rc;
+    if ((rc = up(&d.d_ve_chk, h->ve_chk))) return rc;
+    if (!h->tables.empty()) {
+        CU(cudaMalloc(&d.d_tables, h->tables.size()));
+        CU(cudaMemcpy(d.d_tables, h->tables.data(), h->tables.size(), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc(&d.d_queue, 2 * sizeof(unsigned long long)));
+    CU(cudaMallocHost(&d.h_queue, 2 * sizeof(unsigned long long)));
+    return 0;
+}
+
+void destroy_device(DeviceCtx &d)
+{
+    cudaSetDevice(d.device);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    cudaFree(d.d_rowptr); cudaFree(d.d_colptr); cudaFree(d.d_ve_slot); cudaFree(d.d_ve_chk);
+    cudaFree(d.d_tables); cudaFree(d.d_queue);
+    if (d.h_queue) cudaFreeHost(d.h_queue);
+    for (DevBuf *b : {&d.msg, &d.syn, &d.resid, &d.errb, &d.sid, &d.iter, &d.flags, &d.nnz, &d.raw_in, &d.raw_out,
+                      &d.syn_words, &d.err_words, &d.conv, &d.iters, &d.ratio, &d.counters, &d.scratch})
+        b->release();
+    if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+template <bool BIG>
+int smem_kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
+{
+    CU(cudaFuncSetAttribute(bp::bp_smem_kernel<BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CU(cudaFuncSetAttribute(bp::bp_smem_kernel<BIG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bp::bp_smem_kernel<BIG>, threads, smem_bytes));
+    return 0;
+}
+
+// Resolve family / launch shape from the code size, the options and device 0's limits.
+int configure(ldpcb200 *h)
+{
+    if (h->configured) return 0;
+    DeviceCtx &d0 = h->dev[0];
+    CU(cudaSetDevice(d0.device));
+    bp::SmemParams sp{};
+    const int need = h->tables.empty() ? 0x7fffffff : smem_layout(h, sp);
+    int family = h->opt_family;
+    const bool smem_ok = need <= d0.smem_optin && h->E > 0;
+    if (family == LDPCB200_FAMILY_AUTO) family = smem_ok ? LDPCB200_FAMILY_SMEM : LDPCB200_FAMILY_GLOBAL;
+    if (family == LDPCB200_FAMILY_SMEM && !smem_ok)
+        return fail(LDPCB200_EUNSUPPORTED, "family SMEM needs %d bytes of shared memory per CTA (limit %d)", need,
+                    d0.smem_optin);
+    h->family = family;
+    if (family == LDPCB200_FAMILY_SMEM) {
+        const bool two = 2 * (need + 1024) <= d0.smem_per_sm;
+        int warps = h->opt_warps > 0 ? h->opt_warps : (two ? 8 : 16);
+        warps = std::max(1, std::min(16, warps));
+        int bps = 0, rc;
+        for (DeviceCtx &d : h->dev) {
+            CU(cudaSetDevice(d.device));
+            rc = h->big ? smem_kernel_attrs<true>(need, warps * 32, &bps) : smem_kernel_attrs<false>(need, warps * 32, &bps);
+            if (rc) return rc;
+        }
+        if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "family SMEM kernel does not fit on an SM");
+        h->warps = warps;
+        h->ctas_per_sm = bps;
+        h->smem_bytes = need;
+        h->sp_proto = sp;
+    } else {
+        // resident slots: enough warp-tasks to fill the GPU, messages preferably L2-sized
+        const double bytes_per_slot = static_cast<double>(std::max<int64_t>(h->E, 1)) * 8.0;
+        int64_t slots = h->opt_slots;
+        if (slots <= 0) {
+            const int64_t for_l2 = static_cast<int64_t>(48.0 * 1048576.0 / bytes_per_slot);
+            const int64_t min_par = (static_cast<int64_t>(d0.sm_count) * 48 + std::max<int64_t>(h->s, 1) - 1) /
+                                    std::max<int64_t>(h->s, 1) * 32;
+            slots = std::max(for_l2, min_par);
+            slots = std::min<int64_t>(slots, 16384);
+        }
+        slots = std::max<int64_t>(32, (slots + 31) / 32 * 32);
+        h->slots = static_cast<int>(slots);
+    }
+    h->configured = true;
+    return 0;
+}
+
+int ensure_global_state(ldpcb200 *h, DeviceCtx &d, int nslab)
+{
+    if (nslab <= d.nslab_alloc) return 0;
+    int rc;
+    const size_t ns = static_cast<size_t>(nslab) * 32;
+    if ((rc = d.msg.reserve(static_cast<size_t>(nslab) * std::max<int64_t>(h->E, 1) * 32 * 8))) return rc;
+    if ((rc = d.syn.reserve(static_cast<size_t>(nslab) * h->SW * 128))) return rc;
+    if ((rc = d.resid.reserve(static_cast<size_t>(nslab) * h->SW * 128))) return rc;
+    if ((rc = d.errb.reserve(static_cast<size_t>(nslab) * h->NW * 128))) return rc;
+    if ((rc = d.sid.reserve(ns * 8))) return rc;
+    if ((rc = d.iter.reserve(ns * 4))) return rc;
+    if ((rc = d.flags.reserve(ns * 4))) return rc;
+    if ((rc = d.nnz.reserve(ns * 4))) return rc;
+    d.nslab_alloc = nslab;
+    return 0;
+}
+
+__global__ void add_counters_kernel(unsigned long long *c, unsigned long long decoded)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(c, decoded);
+}
+
+// Decode B syndromes resident on device `d` (native packed rows).  Stream-ordered for family
+// SMEM; family GLOBAL synchronises the stream internally while it polls for completion.
+int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
+                     uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st)
+{
+    if (B <= 0) return 0;
+    CU(cudaSetDevice(d.device));
+    if (h->max_iters <= 0) {
+        // loop at belief_propagation.jl:134 never runs: err stays zero, converged = false
+        CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
+        CU(cudaMemsetAsync(conv, 0, static_cast<size_t>(B), st));
+        if (iters) CU(cudaMemsetAsync(iters, 0, static_cast<size_t>(B) * 4, st));
+        if (ratio) return fail(LDPCB200_EINVAL, "posterior_ratio is undefined for max_iters = 0");
+        if (counters) {
+            add_counters_kernel<<<1, 32, 0, st>>>(counters, static_cast<unsigned long long>(B));
+            h->launches++;
+        }
+        return 0;
+    }
+    if (h->family == LDPCB200_FAMILY_SMEM) {
+        bp::SmemParams p = h->sp_proto;
+        p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
+        p.SW = h->SW; p.NW = h->NW;
+        p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop; p.p0 = h->p0; p.B = B;
+        p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
+        p.counters = counters;
+        p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
+        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve;
+        const long long nchunks = (B + 31) / 32;
+        const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
+        if (h->big)
+            bp::bp_smem_kernel<true><<<grid, h->warps * 32, h->smem_bytes, st>>>(p);
+        else
+            bp::bp_smem_kernel<false><<<grid, h->warps * 32, h->smem_bytes, st>>>(p);
+        h->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    // ---- family GLOBAL
+    const int nslab = static_cast<int>(std::min<int64_t>(h->slots / 32, (B + 31) / 32));
+    int rc = ensure_global_state(h, d, nslab);
+    if (rc) return rc;
+    bp::GlobalParams p{};
+    p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
+    p.SW = h->SW; p.NW = h->NW; p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop;
+    p.nslab = nslab; p.p0 = h->p0; p.B = B;
+    p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
+    p.counters = counters;
+    p.rowptr = d.d_rowptr; p.colptr = d.d_colptr; p.ve_slot = d.d_ve_slot; p.ve_chk = d.d_ve_chk;
+    p.msg = d.msg.as<double>(); p.syn = d.syn.as<uint32_t>(); p.resid = d.resid.as<uint32_t>();
+    p.errb = d.errb.as<uint32_t>(); p.sid = d.sid.as<long long>(); p.iter = d.iter.as<int>();
+    p.flags = d.flags.as<int>(); p.nnz = d.nnz.as<int>(); p.queue = d.d_queue;
+    CU(cudaMemsetAsync(d.d_queue, 0, 2 * sizeof(unsigned long long), st));
+    bp::bp_global_finish<<<nslab, 256, 0, st>>>(p, 1);
+    h->launches++;
+    const long long cwarps = static_cast<long long>(nslab) * h->s, vwarps = static_cast<long long>(nslab) * h->n;
+    const int cap = d.sm_count * 32;
+    const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((cwarps + 7) / 8, cap)));
+    const int vgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((vwarps + 7) / 8, cap)));
+    const long long NS = static_cast<long long>(nslab) * 32;
+    long long finished = 0;
+    while (finished < B) {
+        // at most NS syndromes can finish per iteration: no need to poll before that many ran
+        long long burst = (B - finished + NS - 1) / NS;
+        burst = std::max<long long>(1, std::min<long long>(burst, 64));
+        if (B - finished <= NS) burst = std::min<long long>(burst + 1, std::max(1, h->max_iters / 8 + 1));
+        for (long long it = 0; it < burst; ++it) {
+            if (h->big) {
+                bp::bp_global_check<true><<<cgrid, 256, 0, st>>>(p);
+                bp::bp_global_var<true><<<vgrid, 256, 0, st>>>(p);
+            } else {
+                bp::bp_global_check<false><<<cgrid, 256, 0, st>>>(p);
+                bp::bp_global_var<false><<<vgrid, 256, 0, st>>>(p);
+            }
+            bp::bp_global_finish<<<nslab, 256, 0, st>>>(p, 0);
+            h->launches += 3;
+        }
+        CU(cudaMemcpyAsync(d.h_queue, d.d_queue, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        finished = static_cast<long long>(d.h_queue[1]);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+size_t fmt_bytes(int fmt, int64_t rows, int64_t ld, int64_t B, int RW)
+{
+    switch (fmt) {
+        case LDPCB200_FMT_U8: return static_cast<size_t>(B ? (B - 1) * ld + rows : 0);
+        case LDPCB200_FMT_I64: return static_cast<size_t>(B ? (B - 1) * ld + rows : 0) * 8;
+        case LDPCB200_FMT_F64: return static_cast<size_t>(B ? (B - 1) * ld + rows : 0) * 8;
+        case LDPCB200_FMT_BITS: return static_cast<size_t>((B * rows + 31) / 32) * 4;
+        case LDPCB200_FMT_PACKED32: return static_cast<size_t>(B) * RW * 4;
+    }
+    return 0;
+}
+
+inline int grid_for(long long work, int sm) { return static_cast<int>(std::max<long long>(1, std::min<long long>((work + 255) / 256, static_cast<long long>(sm) * 16))); }
+
+// One device's share [b0, b0+Bd) of a host batch, processed in chunks.
+int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t Btot, const void *syndromes,
+                      int syn_fmt, int64_t syn_ld, void *errors, int err_fmt, int64_t err_ld, uint8_t *converged,
+                      int32_t *iters, double *ratio, int64_t *counters_out)
+{
+    (void)Btot;
+    CU(cudaSetDevice(d.device));
+    const int64_t s = h->s, n = h->n;
+    cudaStream_t st = d.stream;
+    // chunk size: bound the staging footprint
+    const double per_syn = static_cast<double>(fmt_bytes(syn_fmt, s, syn_ld, 2, h->SW) - fmt_bytes(syn_fmt, s, syn_ld, 1, h->SW)) +
+                           static_cast<double>(fmt_bytes(err_fmt, n, err_ld, 2, h->NW) - fmt_bytes(err_fmt, n, err_ld, 1, h->NW)) +
+                           (h->SW + h->NW) * 4.0 + 5.0 + (ratio ? 8.0 * n : 0.0);
+    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : static_cast<int64_t>(512.0 * 1048576.0 / std::max(per_syn, 1.0));
+    CH = std::max<int64_t>(32, std::min<int64_t>(CH, 1 << 22) / 32 * 32);
+    int rc;
+    if ((rc = d.counters.reserve(LDPCB200_NUM_COUNTERS * 8))) return rc;
+    CU(cudaMemsetAsync(d.counters.p, 0, LDPCB200_NUM_COUNTERS * 8, st));
+    for (int64_t c0 = 0; c0 < Bd; c0 += CH) {
+        const int64_t Bc = std::min(CH, Bd - c0);
+        const int64_t g0 = b0 + c0;                       // first global column of this chunk
+        if ((rc = d.syn_words.reserve(static_cast<size_t>(Bc) * h->SW * 4))) return rc;
+        if ((rc = d.err_words.reserve(static_cast<size_t>(Bc) * h->NW * 4))) return rc;
+        if ((rc = d.conv.reserve(static_cast<size_t>(Bc)))) return rc;
+        if ((rc = d.iters.reserve(static_cast<size_t>(Bc) * 4))) return rc;
+        if (ratio && (rc = d.ratio.reserve(static_cast<size_t>(Bc) * n * 8))) return rc;
+        // ---- syndromes -> device -> packed rows
+        uint32_t *syn_words = d.syn_words.as<uint32_t>();
+        if (syn_fmt == LDPCB200_FMT_PACKED32) {
+            CU(cudaMemcpyAsync(syn_words, static_cast<const uint32_t *>(syndromes) + g0 * h->SW,
+                               static_cast<size_t>(Bc) * h->SW * 4, cudaMemcpyHostToDevice, st));
+        } else if (syn_fmt == LDPCB200_FMT_BITS) {
+            const size_t w0 = static_cast<size_t>(g0 * s / 32);           // g0 is a multiple of 32
+            const size_t nw = static_cast<size_t>((Bc * s + 31) / 32);
+            if ((rc = d.raw_in.reserve(nw * 4))) return rc;
+            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const uint32_t *>(syndromes) + w0, nw * 4, cudaMemcpyHostToDevice, st));
+            bp::pack_bits<<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<uint32_t>(), static_cast<long long>(nw),
+                                                                            static_cast<int>(s), h->SW, Bc, syn_words);
+            h->launches++;
+        } else if (syn_fmt == LDPCB200_FMT_U8) {
+            const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
+            if ((rc = d.raw_in.reserve(bytes))) return rc;
+            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const uint8_t *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            bp::pack_elems<uint8_t><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<uint8_t>(), syn_ld,
+                                                                                     static_cast<int>(s), h->SW, Bc, syn_words);
+            h->launches++;
+        } else if (syn_fmt == LDPCB200_FMT_I64) {
+            const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
+            if ((rc = d.raw_in.reserve(bytes))) return rc;
+            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const long long *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            bp::pack_elems<long long><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<long long>(), syn_ld,
+                                                                                       static_cast<int>(s), h->SW, Bc, syn_words);
+            h->launches++;
+        } else {
+            return fail(LDPCB200_EINVAL, "unsupported syndrome format %d", syn_fmt);
+        }
+        // ---- decode
+        rc = decode_on_device(h, d, Bc, syn_words, d.err_words.as<uint32_t>(), d.conv.as<uint8_t>(), d.iters.as<int32_t>(),
+                              ratio ? d.ratio.as<double>() : nullptr, d.counters.as<unsigned long long>(), st);
+        if (rc) return rc;
+        // ---- packed rows -> caller's format -> host
+        const uint32_t *ew = d.err_words.as<uint32_t>();
+        if (err_fmt == LDPCB200_FMT_PACKED32) {
+            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + g0 * h->NW, ew, static_cast<size_t>(Bc) * h->NW * 4,
+                               cudaMemcpyDeviceToHost, st));
+        } else if (err_fmt == LDPCB200_FMT_BITS) {
+            const size_t w0 = static_cast<size_t>(g0 * n / 32);
+            const size_t nw = static_cast<size_t>((Bc * n + 31) / 32);
+            if ((rc = d.raw_out.reserve(nw * 4))) return rc;
+            bp::unpack_bits<<<grid_for(static_cast<long long>(nw), d.sm_count), 256, 0, st>>>(
+                ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<uint32_t>(), static_cast<long long>(nw));
+            h->launches++;
+            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + w0, d.raw_out.p, nw * 4, cudaMemcpyDeviceToHost, st));
+        } else if (err_fmt == LDPCB200_FMT_U8 || err_fmt == LDPCB200_FMT_I64 || err_fmt == LDPCB200_FMT_F64) {
+            const size_t bytes = fmt_bytes(err_fmt, n, err_ld, Bc, h->NW);
+            if ((rc = d.raw_out.reserve(bytes))) return rc;
+            const int g = grid_for(Bc * h->NW, d.sm_count);
+            if (err_ld != n) CU(cudaMemsetAsync(d.raw_out.p, 0, bytes, st));
+            if (err_fmt == LDPCB200_FMT_U8)
+                bp::unpack_elems<uint8_t><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<uint8_t>(), err_ld);
+            else if (err_fmt == LDPCB200_FMT_I64)
+                bp::unpack_elems<long long><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<long long>(), err_ld);
+            else
+                bp::unpack_elems<double><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<double>(), err_ld);
+            h->launches++;
+            const size_t esz = err_fmt == LDPCB200_FMT_U8 ? 1 : 8;
+            if (err_ld == n) {
+                CU(cudaMemcpyAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, d.raw_out.p, bytes,
+                                   cudaMemcpyDeviceToHost, st));
+            } else {   // strided destination: only the n rows of each column belong to the caller
+                CU(cudaMemcpy2DAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, err_ld * esz,
+                                     d.raw_out.p, err_ld * esz, n * esz, Bc, cudaMemcpyDeviceToHost, st));
+            }
+        } else {
+            return fail(LDPCB200_EINVAL, "unsupported error format %d", err_fmt);
+        }
+        CU(cudaMemcpyAsync(converged + g0, d.conv.p, static_cast<size_t>(Bc), cudaMemcpyDeviceToHost, st));
+        if (iters) CU(cudaMemcpyAsync(iters + g0, d.iters.p, static_cast<size_t>(Bc) * 4, cudaMemcpyDeviceToHost, st));
+        if (ratio) CU(cudaMemcpyAsync(ratio + g0 * n, d.ratio.p, static_cast<size_t>(Bc) * n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    unsigned long long hc[LDPCB200_NUM_COUNTERS];
+    CU(cudaMemcpyAsync(hc, d.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < LDPCB200_NUM_COUNTERS; ++k) counters_out[k] = static_cast<int64_t>(hc[k]);
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char *ldpcb200_last_error(void) { return g_err.c_str(); }
+
+int ldpcb200_version(void) { return 100; }
+
+int ldpcb200_device_count(int32_t *out)
+{
+    if (!out) return fail(LDPCB200_EINVAL, "out is null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return fail(LDPCB200_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return 0;
+}
+
+int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval, int32_t index_base, double per,
+                    int32_t max_iters, int32_t variant, const int32_t *devices, int32_t ndev, ldpcb200_t **out)
+{
+    if (!out) return fail(LDPCB200_EINVAL, "out is null");
+    *out = nullptr;
+    if (s < 0 || n < 0 || !colptr || (index_base != 0 && index_base != 1))
+        return fail(LDPCB200_EINVAL, "bad shape / null colptr / index_base not 0 or 1");
+    if (s > 0x3fffffff || n > 0x3fffffff) return fail(LDPCB200_EINVAL, "matrix too large");
+    if (!rowval && colptr[n] - index_base != 0) return fail(LDPCB200_EINVAL, "rowval is null");
+    if (variant != LDPCB200_VARIANT_EXACT) return fail(LDPCB200_EUNSUPPORTED, "variant %d not available", variant);
+    if (max_iters < 0) max_iters = 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(LDPCB200_ENODEVICE, "no CUDA device available (%s); libldpcb200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    ldpcb200 *h = new ldpcb200();
+    h->s = s; h->n = n; h->per = per; h->max_iters = max_iters; h->variant = variant;
+    // channel_probs[j] / (1 - channel_probs[j]) (belief_propagation.jl:129,153), IEEE double on the host
+    {
+        volatile double one_minus = 1.0 - per;
+        volatile double q = per / one_minus;
+        h->p0 = q;
+    }
+    int rc = build_graph(h, colptr, rowval, index_base);
+    if (rc) { delete h; return rc; }
+    std::vector<int> devs;
+    if (devices && ndev > 0) devs.assign(devices, devices + ndev); else devs.push_back(0);
+    for (int dv : devs) {
+        if (dv < 0 || dv >= count) { delete h; return fail(LDPCB200_ENODEVICE, "device %d not present (%d devices)", dv, count); }
+    }
+    h->dev.resize(devs.size());
+    for (size_t k = 0; k < devs.size(); ++k) {
+        h->dev[k].device = devs[k];
+        rc = init_device(h, h->dev[k]);
+        if (rc) { ldpcb200_destroy(h); return rc; }
+    }
+    *out = h;
+    return 0;
+}
+
+int ldpcb200_destroy(ldpcb200_t *h)
+{
+    if (!h) return 0;
+    for (DeviceCtx &d : h->dev) destroy_device(d);
+    delete h;
+    return 0;
+}
+
+int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
+{
+    if (!h || !key) return fail(LDPCB200_EINVAL, "null handle or key");
+    const std::string k(key);
+    if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration
+    if (k == "chunk") { h->opt_chunk = value; return 0; }
+    if (k == "family") h->opt_family = static_cast<int>(value);
+    else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "slots") h->opt_slots = static_cast<int>(value);
+    else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
+    h->configured = false;
+    return 0;
+}
+
+int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
+{
+    if (!hc || !out) return fail(LDPCB200_EINVAL, "null argument");
+    ldpcb200 *h = const_cast<ldpcb200 *>(hc);
+    int rc = configure(h);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->s = h->s; out->n = h->n; out->E = h->E;
+    out->max_check_degree = h->max_cdeg; out->max_var_degree = h->max_vdeg;
+    out->family = h->family; out->ndev = static_cast<int>(h->dev.size());
+    out->sm_count = h->dev[0].sm_count;
+    out->ctas_per_sm = h->ctas_per_sm; out->threads_per_cta = h->family == LDPCB200_FAMILY_SMEM ? h->warps * 32 : 256;
+    out->smem_bytes = h->smem_bytes; out->slots = h->slots;
+    out->syn_words = h->SW; out->err_words = h->NW;
+    out->message_bytes = h->family == LDPCB200_FAMILY_SMEM
+                             ? 0
+                             : static_cast<int64_t>(h->slots) * std::max<int64_t>(h->E, 1) * 8;
+    return 0;
+}
+
+int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_syn_words, uint32_t *d_err_words,
+                           uint8_t *d_converged, int32_t *d_iters, double *d_posterior_ratio,
+                           unsigned long long *d_counters, void *stream)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad dev_slot");
+    if (B < 0 || (B > 0 && (!d_syn_words || !d_err_words || !d_converged))) return fail(LDPCB200_EINVAL, "null device buffer");
+    int rc = configure(h);
+    if (rc) return rc;
+    DeviceCtx &d = h->dev[dev_slot];
+    return decode_on_device(h, d, B, d_syn_words, d_err_words, d_converged, d_iters, d_posterior_ratio, d_counters,
+                            stream ? static_cast<cudaStream_t>(stream) : d.stream);
+}
+
+int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
+                          int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *posterior_ratio,
+                          int64_t *counters)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (B < 0) return fail(LDPCB200_EINVAL, "negative batch");
+    if (counters) memset(counters, 0, sizeof(int64_t) * LDPCB200_NUM_COUNTERS);
+    if (B == 0) return 0;
+    if (!syndromes || !errors || !converged) return fail(LDPCB200_EINVAL, "null host buffer");
+    if (syn_fmt == LDPCB200_FMT_F64) return fail(LDPCB200_EINVAL, "FMT_F64 is an output-only format");
+    if ((syn_fmt == LDPCB200_FMT_U8 || syn_fmt == LDPCB200_FMT_I64) && syn_ld < h->s) return fail(LDPCB200_EINVAL, "syn_ld < s");
+    if ((err_fmt == LDPCB200_FMT_U8 || err_fmt == LDPCB200_FMT_I64 || err_fmt == LDPCB200_FMT_F64) && err_ld < h->n)
+        return fail(LDPCB200_EINVAL, "err_ld < n");
+    int rc = configure(h);
+    if (rc) return rc;
+    const int nd = static_cast<int>(h->dev.size());
+    // contiguous column ranges per device, boundaries multiples of 32 (bit formats stay word aligned)
+    std::vector<int64_t> lo(nd + 1, 0);
+    const int64_t blocks = (B + 31) / 32;
+    for (int k = 0; k <= nd; ++k) lo[k] = std::min<int64_t>(B, (blocks * k / nd) * 32);
+    lo[nd] = B;
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<int64_t> ctr(static_cast<size_t>(nd) * LDPCB200_NUM_COUNTERS, 0);
+    auto work = [&](int k) {
+        if (lo[k + 1] > lo[k])
+            rcs[k] = decode_host_range(h, h->dev[k], lo[k], lo[k + 1] - lo[k], B, syndromes, syn_fmt, syn_ld, errors, err_fmt,
+                                       err_ld, converged, iters, posterior_ratio, &ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS]);
+        if (rcs[k]) errs[k] = g_err;
+    };
+    if (nd == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nd; ++k) th.emplace_back(work, k);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < nd; ++k)
+        if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    if (counters)
+        for (int k = 0; k < nd; ++k)
+            for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) counters[c] += ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS + c];
+    return 0;
+}
+
+int ldpcb200_sample_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, int64_t first, uint64_t seed, double per,
+                           uint32_t *d_true_err_words, uint32_t *d_syn_words, void *stream)
+{
+    if (!h || dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad handle / dev_slot");
+    if (B <= 0) return 0;
+    if (!d_true_err_words || !d_syn_words) return fail(LDPCB200_EINVAL, "null device buffer");
+    DeviceCtx &d = h->dev[dev_slot];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
+    double t = std::floor(per * 4294967296.0);
+    uint32_t thr = !(t > 0) ? 0u : (t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t));
+    CU(cudaMemsetAsync(d_syn_words, 0, static_cast<size_t>(B) * h->SW * 4, st));
+    bp::sample_errors<<<grid_for(B * h->NW, d.sm_count), 256, 0, st>>>(static_cast<int>(h->n), h->NW, B, first,
+                                                                      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+                                                                      thr, d_true_err_words);
+    bp::syndrome_of<<<grid_for(B * h->NW, d.sm_count), 256, 0, st>>>(d.d_colptr, d.d_ve_chk, h->NW, h->SW, B, d_true_err_words,
+                                                                    d_syn_words);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_true_err_words,
+                          const uint32_t *d_err_words, const uint32_t *d_syn_words, unsigned long long *d_out, void *stream)
+{
+    if (!h || dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad handle / dev_slot");
+    if (B <= 0) return 0;
+    if (!d_true_err_words || !d_err_words || !d_syn_words || !d_out) return fail(LDPCB200_EINVAL, "null device buffer");
+    DeviceCtx &d = h->dev[dev_slot];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
+    int rc = d.scratch.reserve(static_cast<size_t>(B) * h->SW * 4);
+    if (rc) return rc;
+    bp::score_rows<<<grid_for(B * 32, d.sm_count), 256, 0, st>>>(d.d_rowptr, d.d_colptr, d.d_ve_chk, h->NW, h->SW, B,
+                                                                d_true_err_words, d_err_words, d_syn_words,
+                                                                d.scratch.as<uint32_t>(), d_out);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ldpcb200_launch_count(const ldpcb200_t *h, int64_t *out)
+{
+    if (!h || !out) return fail(LDPCB200_EINVAL, "null argument");
+    *out = h->launches.load();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+"""Independent dense transliteration of the reference decode! (TEST INFRASTRUCTURE ONLY).
+
+A second, deliberately naive restatement used to cross-check oracle/bp_oracle.c on small
+cases: dense s x n float64 matrices, 1:1 with
+/root/reference/src/decoders/belief_propagation.jl:121-188 (same loop nests, same operand order).
+Pure-Python loops -> small cases only.
+"""
+import numpy as np
+
+
+def decode_dense(H, per, max_iters, syndrome):
+    """Returns (err float64[n] of 0.0/1.0, converged bool, ratio float64[n], iters int)."""
+    H = np.asarray(H).astype(np.int64)
+    s, n = H.shape
+    f = np.float64
+    one, two = f(1.0), f(2.0)
+    per = f(per)
+    rows_of_col = [np.nonzero(H[:, j])[0] for j in range(n)]   # rowvals/nzrange of sparse_H
+    cols_of_row = [np.nonzero(H[i, :])[0] for i in range(s)]   # rowvals/nzrange of sparse_HT
+    # reset! (:83-91)
+    log_ratio = np.ones(n, dtype=f)
+    channel = np.full(n, per, dtype=f)
+    b2c = np.zeros((s, n), dtype=f)
+    c2b = np.zeros((s, n), dtype=f)
+    err = np.zeros(n, dtype=f)
+    with np.errstate(all="ignore"):
+        for j in range(n):                                       # :127-131
+            for i in rows_of_col[j]:
+                b2c[i, j] = channel[j] / (one - channel[j])
+        converged = False
+        iters = 0
+        for it in range(1, max_iters + 1):                       # :134
+            iters = it
+            for i in range(s):                                   # :135-150
+                temp = f(-1.0) if int(syndrome[i]) % 2 else one  # (-1)^syndrome[i]
+                for j in cols_of_row[i]:
+                    c2b[i, j] = temp
+                    temp = temp * (two / (one + b2c[i, j]) - one)
+                temp = one
+                for j in cols_of_row[i][::-1]:
+                    c2b[i, j] = c2b[i, j] * temp
+                    c2b[i, j] = (one - c2b[i, j]) / (one + c2b[i, j])
+                    temp = temp * (two / (one + b2c[i, j]) - one)
+            for j in range(n):                                   # :152-178
+                temp = channel[j] / (one - channel[j])
+                for i in rows_of_col[j]:
+                    b2c[i, j] = temp
+                    temp = temp * c2b[i, j]
+                    if np.isnan(temp):
+                        temp = one
+                log_ratio[j] = temp                              # reference keeps log(1/temp)
+                err[j] = 1.0 if temp >= 1 else 0.0
+                temp = one
+                for i in rows_of_col[j][::-1]:
+                    b2c[i, j] = b2c[i, j] * temp
+                    temp = temp * c2b[i, j]
+                    if np.isnan(temp):
+                        temp = one
+            decoded = (H @ err.astype(np.int64)) % 2             # :180
+            if np.all(decoded == np.asarray(syndrome).astype(np.int64)):   # :181
+                converged = True
+                break
+    return err, converged, log_ratio, iters
+
+
+def brute_force_ratio(H, per, syndrome):
+    """Exact posterior ratios P(e_j=1|s)/P(e_j=0|s) by enumeration (n <= ~20).
+    BP is exact on cycle-free Tanner graphs, so this is a known-answer test there."""
+    H = np.asarray(H).astype(np.int64)
+    s, n = H.shape
+    syndrome = np.asarray(syndrome).astype(np.int64)
+    p1 = np.zeros(n)
+    p0 = np.zeros(n)
+    for m in range(1 << n):
+        e = np.array([(m >> j) & 1 for j in range(n)], dtype=np.int64)
+        if np.any((H @ e) % 2 != syndrome):
+            continue
+        w = int(e.sum())
+        pr = per ** w * (1 - per) ** (n - w)
+        p1 += pr * e
+        p0 += pr * (1 - e)
+    with np.errstate(all="ignore"):
+        return p1 / p0

@@ -1,0 +1,341 @@
+/*
+ * bp_oracle.c -- CPU restatement of LDPCDecoders.jl's belief-propagation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (ldpcdecoders.jl_b200/,
+ * libldpcb200.so) may include, link or call this file.  It is used by tests/,
+ * __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py.
+ *
+ * PARITY UNPINNED: the reference (pure Julia) cannot be executed in this image
+ * (no julia binary, no network) and its test-suite holds no golden vectors for this
+ * path (all inputs come from an unseeded RNG, /root/reference/test/test_bp_decoder.jl:7-9).
+ * This restatement is therefore pinned only by (i) line-by-line correspondence with the
+ * cited reference lines, (ii) brute-force marginal KATs on cycle-free graphs,
+ * (iii) an independent dense transliteration (oracle/bp_dense.py) and (iv) the
+ * reference's statistical acceptance thresholds.  oracle/dump_golden.jl regenerates
+ * golden vectors from the real package for anyone who has Julia.
+ *
+ * What is restated (all citations relative to /root/reference/):
+ *   src/decoders/belief_propagation.jl:83-91    reset!   (scratch zeroed, priors refilled)
+ *   src/decoders/belief_propagation.jl:127-131  message initialisation  b2c = p/(1-p)
+ *   src/decoders/belief_propagation.jl:135-150  check update (ratio domain, prefix/suffix)
+ *   src/decoders/belief_propagation.jl:152-178  variable update, hard decision, NaN clamp
+ *   src/decoders/belief_propagation.jl:180-184  syndrome re-check and early break
+ *   src/decoders/belief_propagation.jl:220-231  batchdecode! column loop
+ *
+ * Arithmetic: IEEE-754 binary64, round-to-nearest, every operation rounded
+ * separately (compile with -O2 -ffp-contract=off -fno-fast-math on x86-64/SSE2).
+ *
+ * Two storage modes with bit-identical results:
+ *   dense = 0 : messages stored per edge (E doubles each direction)
+ *   dense = 1 : "faithful cost" -- two dense s*n column-major matrices that are
+ *               zero-filled on every decode and a per-iteration H*err mat-vec with
+ *               fresh allocations, mimicking what the Julia package does per call.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int64_t s, n, E;
+    const int64_t *colptr;   /* n+1, 0-based: column j of H = edges [colptr[j], colptr[j+1]) */
+    const int64_t *rowval;   /* E, 0-based check index, ascending inside a column (SparseMatrixCSC invariant) */
+    int64_t *rowptr;         /* s+1: row i of H (= column i of sparse_HT) */
+    int64_t *rowvar;         /* E: variable index, ascending inside a row */
+    int64_t *rowedge;        /* E: CSC position of that (i,j) entry */
+} graph_t;
+
+static int build_graph(graph_t *g, int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval)
+{
+    g->s = s; g->n = n; g->E = colptr[n];
+    g->colptr = colptr; g->rowval = rowval;
+    g->rowptr = (int64_t *)calloc((size_t)s + 1, sizeof(int64_t));
+    g->rowvar = (int64_t *)malloc(sizeof(int64_t) * (size_t)(g->E ? g->E : 1));
+    g->rowedge = (int64_t *)malloc(sizeof(int64_t) * (size_t)(g->E ? g->E : 1));
+    if (!g->rowptr || !g->rowvar || !g->rowedge) return -1;
+    for (int64_t e = 0; e < g->E; ++e) {
+        if (rowval[e] < 0 || rowval[e] >= s) return -2;
+        g->rowptr[rowval[e] + 1]++;
+    }
+    for (int64_t i = 0; i < s; ++i) g->rowptr[i + 1] += g->rowptr[i];
+    int64_t *fill = (int64_t *)malloc(sizeof(int64_t) * (size_t)(s ? s : 1));
+    if (!fill) return -1;
+    memcpy(fill, g->rowptr, sizeof(int64_t) * (size_t)s);
+    /* columns visited in ascending j => variables ascending inside every row,
+       which is the order nzrange(sparse_HT, i) walks (belief_propagation.jl:137). */
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t e = colptr[j]; e < colptr[j + 1]; ++e) {
+            int64_t i = rowval[e];
+            g->rowvar[fill[i]] = j;
+            g->rowedge[fill[i]] = e;
+            fill[i]++;
+        }
+    free(fill);
+    return 0;
+}
+
+static void free_graph(graph_t *g) { free(g->rowptr); free(g->rowvar); free(g->rowedge); }
+
+/* One decode!, edge-indexed storage.  b2c/c2b are indexed by CSC edge position.
+ * syn: s bytes (0/1).  err: n bytes out.  ratio: n doubles out or NULL (posterior
+ * ratio R_j; the reference stores log(1/R_j), belief_propagation.jl:163).
+ * Returns converged flag; *iters_out = iterations executed. */
+static int decode_edge(const graph_t *g, double per, int max_iters, const uint8_t *syn,
+                       double *b2c, double *c2b, uint8_t *err, double *ratio, int32_t *iters_out)
+{
+    const int64_t s = g->s, n = g->n;
+    /* reset! : belief_propagation.jl:83-91 (err .= 0; messages are fully rewritten below) */
+    memset(err, 0, (size_t)n);
+    if (ratio) for (int64_t j = 0; j < n; ++j) ratio[j] = 1.0; /* log_probabs .= 0  <=> ratio 1 */
+    /* init : belief_propagation.jl:127-131 */
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e)
+            b2c[e] = per / (1 - per);
+
+    int converged = 0;
+    int32_t it = 0;
+    for (int iter = 1; iter <= max_iters; ++iter) {            /* :134 */
+        it = iter;
+        for (int64_t i = 0; i < s; ++i) {                      /* :135 */
+            double temp = syn[i] ? -1.0 : 1.0;                 /* (-1)^syndrome[i], :136 */
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) {      /* :137-141 */
+                int64_t e = g->rowedge[k];
+                c2b[e] = temp;
+                temp *= 2 / (1 + b2c[e]) - 1;
+            }
+            temp = 1.0;                                        /* :143 */
+            for (int64_t k = g->rowptr[i + 1] - 1; k >= g->rowptr[i]; --k) { /* :144-149 */
+                int64_t e = g->rowedge[k];
+                c2b[e] *= temp;
+                c2b[e] = (1 - c2b[e]) / (1 + c2b[e]);
+                temp *= 2 / (1 + b2c[e]) - 1;
+            }
+        }
+        for (int64_t j = 0; j < n; ++j) {                      /* :152 */
+            double temp = per / (1 - per);                     /* :153 */
+            for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e) {      /* :155-161 */
+                b2c[e] = temp;
+                temp *= c2b[e];
+                if (temp != temp) temp = 1.0;
+            }
+            if (ratio) ratio[j] = temp;                        /* :163 stores log(1/temp) */
+            err[j] = (temp >= 1) ? 1 : 0;                      /* :164-168 */
+            temp = 1.0;                                        /* :170 */
+            for (int64_t e = g->colptr[j + 1] - 1; e >= g->colptr[j]; --e) { /* :171-177 */
+                b2c[e] *= temp;
+                temp *= c2b[e];
+                if (temp != temp) temp = 1.0;
+            }
+        }
+        /* :180-184  (sparse_H * err) .% 2 == syndrome */
+        int ok = 1;
+        for (int64_t i = 0; i < s && ok; ++i) {
+            unsigned par = 0;
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) par ^= err[g->rowvar[k]];
+            if (par != (unsigned)syn[i]) ok = 0;
+        }
+        if (ok) { converged = 1; break; }
+    }
+    if (iters_out) *iters_out = (max_iters > 0) ? it : 0;
+    return converged;
+}
+
+/* One decode!, dense "faithful cost" storage: two s*n column-major matrices exactly like
+ * BeliefPropagationScratchSpace (belief_propagation.jl:3-22), full reset per call (:83-91),
+ * and the allocating mat-vec of :180-181. */
+static int decode_dense(const graph_t *g, double per, int max_iters, const uint8_t *syn,
+                        double *B2C, double *C2B, double *errd, double *chan, double *logp,
+                        uint8_t *err, double *ratio, int32_t *iters_out)
+{
+    const int64_t s = g->s, n = g->n;
+    for (int64_t j = 0; j < n; ++j) logp[j] = 0.0;
+    for (int64_t j = 0; j < n; ++j) chan[j] = per;
+    memset(B2C, 0, sizeof(double) * (size_t)s * (size_t)n);
+    memset(C2B, 0, sizeof(double) * (size_t)s * (size_t)n);
+    for (int64_t j = 0; j < n; ++j) errd[j] = 0.0;
+    if (ratio) for (int64_t j = 0; j < n; ++j) ratio[j] = 1.0;
+#define AT(M, i, j) (M)[(size_t)(i) + (size_t)(j) * (size_t)s]
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e)
+            AT(B2C, g->rowval[e], j) = chan[j] / (1 - chan[j]);
+    int converged = 0;
+    int32_t it = 0;
+    for (int iter = 1; iter <= max_iters; ++iter) {
+        it = iter;
+        for (int64_t i = 0; i < s; ++i) {
+            double temp = syn[i] ? -1.0 : 1.0;
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) {
+                int64_t j = g->rowvar[k];
+                AT(C2B, i, j) = temp;
+                temp *= 2 / (1 + AT(B2C, i, j)) - 1;
+            }
+            temp = 1.0;
+            for (int64_t k = g->rowptr[i + 1] - 1; k >= g->rowptr[i]; --k) {
+                int64_t j = g->rowvar[k];
+                AT(C2B, i, j) *= temp;
+                AT(C2B, i, j) = (1 - AT(C2B, i, j)) / (1 + AT(C2B, i, j));
+                temp *= 2 / (1 + AT(B2C, i, j)) - 1;
+            }
+        }
+        for (int64_t j = 0; j < n; ++j) {
+            double temp = chan[j] / (1 - chan[j]);
+            for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e) {
+                int64_t i = g->rowval[e];
+                AT(B2C, i, j) = temp;
+                temp *= AT(C2B, i, j);
+                if (temp != temp) temp = 1.0;
+            }
+            logp[j] = log(1 / temp);
+            if (ratio) ratio[j] = temp;
+            errd[j] = (temp >= 1) ? 1.0 : 0.0;
+            temp = 1.0;
+            for (int64_t e = g->colptr[j + 1] - 1; e >= g->colptr[j]; --e) {
+                int64_t i = g->rowval[e];
+                AT(B2C, i, j) *= temp;
+                temp *= AT(C2B, i, j);
+                if (temp != temp) temp = 1.0;
+            }
+        }
+#undef AT
+        /* syndrome_decoded = (sparse_H * err) .% 2 ; all(syndrome_decoded .== syndrome) */
+        double *prod = (double *)calloc((size_t)(s ? s : 1), sizeof(double));
+        double *mod2 = (double *)malloc(sizeof(double) * (size_t)(s ? s : 1));
+        uint8_t *eq = (uint8_t *)malloc((size_t)(s ? s : 1));
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e)
+                prod[g->rowval[e]] += errd[j];
+        int ok = 1;
+        for (int64_t i = 0; i < s; ++i) mod2[i] = fmod(prod[i], 2.0);
+        for (int64_t i = 0; i < s; ++i) eq[i] = (mod2[i] == (double)syn[i]);
+        for (int64_t i = 0; i < s; ++i) ok &= eq[i];
+        free(prod); free(mod2); free(eq);
+        if (ok) { converged = 1; break; }
+    }
+    for (int64_t j = 0; j < n; ++j) err[j] = (uint8_t)(errd[j] != 0.0);
+    if (iters_out) *iters_out = (max_iters > 0) ? it : 0;
+    return converged;
+}
+
+/* batchdecode! : belief_propagation.jl:220-231.
+ * syn  : s x B bytes, column-major (column b = syndrome b), values 0/1
+ * err  : n x B bytes out, column-major
+ * conv : B bytes out
+ * iters: B int32 out or NULL ; ratio: n x B doubles out or NULL
+ * nthreads: 1 = what the reference does (serial); >1 = one private scratch per thread.
+ * Returns 0 on success. */
+int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                    double per, int32_t max_iters, int64_t B,
+                    const uint8_t *syn, uint8_t *err, uint8_t *conv,
+                    int32_t *iters, double *ratio, int32_t nthreads, int32_t dense)
+{
+    graph_t g;
+    int rc = build_graph(&g, s, n, colptr, rowval);
+    if (rc) return rc;
+    if (nthreads < 1) nthreads = 1;
+    int fail = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        double *a = NULL, *b = NULL, *errd = NULL, *chan = NULL, *logp = NULL;
+        size_t msz = dense ? (size_t)s * (size_t)n : (size_t)g.E;
+        if (msz == 0) msz = 1;
+        a = (double *)malloc(sizeof(double) * msz);
+        b = (double *)malloc(sizeof(double) * msz);
+        errd = (double *)malloc(sizeof(double) * (size_t)(n ? n : 1));
+        chan = (double *)malloc(sizeof(double) * (size_t)(n ? n : 1));
+        logp = (double *)malloc(sizeof(double) * (size_t)(n ? n : 1));
+        if (!a || !b || !errd || !chan || !logp) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            fail = 1;
+        } else {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+            for (int64_t c = 0; c < B; ++c) {
+                const uint8_t *sc = syn + (size_t)c * (size_t)s;
+                uint8_t *ec = err + (size_t)c * (size_t)n;
+                double *rc_ = ratio ? ratio + (size_t)c * (size_t)n : NULL;
+                int32_t itc = 0;
+                int cv = dense ? decode_dense(&g, per, max_iters, sc, a, b, errd, chan, logp, ec, rc_, &itc)
+                               : decode_edge(&g, per, max_iters, sc, a, b, ec, rc_, &itc);
+                conv[c] = (uint8_t)cv;
+                if (iters) iters[c] = itc;
+            }
+        }
+        free(a); free(b); free(errd); free(chan); free(logp);
+    }
+    free_graph(&g);
+    return fail ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic inputs: i.i.d. Bernoulli(per) bit-flips from Philox4x32-10, keyed by the global
+ * syndrome index so that any sharding of the batch sees the same inputs
+ * (SURVEY.md section 8d).  counter = (b_lo, b_hi, g, 0), key = (seed_lo, seed_hi);
+ * the four 32-bit outputs decide bits 4g..4g+3:  e = (out < floor(per * 2^32)).
+ * The CUDA sampler in the library (ldpcb200_sample) implements the same stream and is
+ * checked against this one.
+ * ---------------------------------------------------------------------------------- */
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                 uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+uint32_t bp_oracle_threshold(double per)
+{
+    double t = floor(per * 4294967296.0);
+    if (!(t > 0)) return 0;
+    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)t;
+}
+
+/* Fills true errors (n x B bytes, column-major) and syndromes (s x B bytes) for global
+ * syndrome indices first .. first+B-1. */
+int bp_oracle_sample(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                     double per, uint64_t seed, int64_t first, int64_t B,
+                     uint8_t *errs, uint8_t *syn)
+{
+    uint32_t thr = bp_oracle_threshold(per);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int64_t c = 0; c < B; ++c) {
+        uint64_t gb = (uint64_t)(first + c);
+        uint8_t *ec = errs + (size_t)c * (size_t)n;
+        uint8_t *sc = syn + (size_t)c * (size_t)s;
+        memset(sc, 0, (size_t)s);
+        for (int64_t g = 0; 4 * g < n; ++g) {
+            uint32_t o[4];
+            philox4x32_10((uint32_t)gb, (uint32_t)(gb >> 32), (uint32_t)g, 0u, k0, k1, o);
+            for (int i = 0; i < 4 && 4 * g + i < n; ++i) ec[4 * g + i] = (uint8_t)(o[i] < thr);
+        }
+        for (int64_t j = 0; j < n; ++j)
+            if (ec[j])
+                for (int64_t e = colptr[j]; e < colptr[j + 1]; ++e) sc[rowval[e]] ^= 1;
+    }
+    return 0;
+}
+
+int bp_oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,67 @@
+"""The C-ABI library loads and exports every symbol include/ldpcb200.h declares; without a GPU
+it refuses to work instead of falling back to anything."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "ldpcb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ldpcb200_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(pkg):
+    assert header_functions() == sorted(pkg._lib.SYMBOLS)
+
+
+def test_library_exports_every_symbol(pkg):
+    lib = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert pkg._lib.load().ldpcb200_version() >= 100
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "ldpcdecoders.jl_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f
+                assert not re.search(r"#\s*include[^\n]*oracle", src), f
+                assert "libbporacle" not in src and "bp_oracle_batch" not in src, f
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_gpu_means_loud_failure(pkg, codes):
+    H = codes.gross_x()
+    with pytest.raises(pkg._lib.LibraryError) as ei:
+        pkg.BeliefPropagationDecoder(H, 0.01, 32)
+    assert ei.value.code == pkg._lib.ENODEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_constructor_argument_types(pkg, codes):
+    H = codes.gross_x()
+    with pytest.raises(TypeError):
+        pkg.BeliefPropagationDecoder(H, 1, 32)          # per::Float64
+    with pytest.raises(TypeError):
+        pkg.BeliefPropagationDecoder(H, 0.01, 32.0)     # max_iters::Int
+
+
+def test_bad_arguments_are_reported_not_crashed(pkg):
+    lib = pkg._lib.load()
+    h = ctypes.c_void_p()
+    colptr = np.array([0, 1], dtype=np.int64)
+    rc = lib.ldpcb200_create(1, 1, colptr.ctypes.data, None, 0, 0.1, 5, 0, None, 0, ctypes.byref(h))
+    assert rc != 0 and lib.ldpcb200_last_error()
+    rc = lib.ldpcb200_create(1, 1, colptr.ctypes.data, colptr.ctypes.data, 7, 0.1, 5, 0, None, 0, ctypes.byref(h))
+    assert rc == pkg._lib.EINVAL
+    assert lib.ldpcb200_destroy(None) == 0

@@ -1,0 +1,289 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes mirror), against the
+CPU oracle on identical (H, per, max_iters, syndromes).  Bar: hard decisions, convergence flags,
+executed iterations and posterior ratios are BIT-EXACT (the kernels replay the reference's FP64
+operation sequence, so no tie tolerance is needed or used)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMEM, GLOBAL = 1, 2
+
+
+def run_gpu(pkg, H, per, max_iters, syn, family=0, want_ratio=False, fmt="u8", **opts):
+    dec = pkg.BeliefPropagationDecoder(H, per, max_iters, family=family, **opts)
+    s, n = H.shape
+    B = syn.shape[1]
+    dt = {"u8": np.uint8, "i64": np.int64, "bool": np.bool_}[fmt]
+    errors = np.full((n, B), 7, dtype=dt, order="F") if fmt != "bool" else np.ones((n, B), dtype=dt, order="F")
+    iters = np.full(B, -1, dtype=np.int32)
+    ratio = np.zeros((n, B), dtype=np.float64, order="F") if want_ratio else None
+    _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn.astype(dt)), errors, iters=iters, posterior_ratio=ratio)
+    info = dec.info()
+    counters = dec.last_counters.copy()
+    dec.close()
+    return dict(errors=errors.astype(np.uint8), converged=success, iters=iters, ratio=ratio, info=info, counters=counters)
+
+
+def assert_same(g, r, want_ratio=False):
+    bad = np.nonzero((g["errors"] != r["errors"]).any(axis=0) | (g["converged"] != r["converged"]) | (g["iters"] != r["iters"]))[0]
+    assert bad.size == 0, "mismatching syndromes: %s (of %d)" % (bad[:10], g["errors"].shape[1])
+    if want_ratio:
+        assert np.array_equal(g["ratio"].view(np.uint64), r["ratio"].view(np.uint64))
+    B = g["errors"].shape[1]
+    assert g["counters"][0] == B
+    assert g["counters"][1] == int(r["converged"].sum())
+    assert g["counters"][2] == int(r["iters"].sum())
+
+
+CASES = [
+    # name, per, B, families
+    ("C3", 0.01, 3000, (SMEM, GLOBAL)),
+    ("C3", 0.05, 3000, (SMEM, GLOBAL)),
+    ("C3", 0.10, 2000, (SMEM, GLOBAL)),
+    ("C2", 0.001, 2000, (SMEM,)),
+    ("C2", 0.03, 3000, (SMEM, GLOBAL)),
+    ("C2", 0.10, 2000, (SMEM,)),
+    ("C4", 0.02, 600, (GLOBAL,)),
+    ("C4", 0.05, 400, (GLOBAL,)),
+    ("C1", 0.01, 200, (GLOBAL,)),
+    ("C1", 0.04, 100, (GLOBAL,)),
+]
+
+
+@pytest.mark.parametrize("name,per,B,families", CASES)
+def test_parity_configs(pkg, oracle, codes, name, per, B, families):
+    H, _, mi = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 12345, 0, B)
+    ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads(), want_ratio=True)
+    for fam in families:
+        g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True)
+        assert g["info"]["family"] == fam
+        assert_same(g, ref, want_ratio=True)
+
+
+def test_parity_c5_large_code(pkg, oracle, codes):
+    H, per, mi = codes.config_matrix("C5")
+    B = 40
+    _, syn = oracle.sample(H, per, 12345, 0, B)
+    ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads())
+    g = run_gpu(pkg, H, per, mi, syn)
+    assert g["info"]["family"] == GLOBAL
+    assert_same(g, ref)
+    # harder channel: some syndromes must run many iterations
+    _, syn = oracle.sample(H, 0.07, 777, 0, 16)
+    ref = oracle.batch_decode(H, 0.07, mi, syn, nthreads=oracle.num_threads())
+    g = run_gpu(pkg, H, 0.07, mi, syn, slots=32)
+    assert_same(g, ref)
+
+
+def test_auto_family_selection(pkg, codes):
+    for name, fam in (("C2", SMEM), ("C3", SMEM), ("C4", GLOBAL), ("C1", GLOBAL)):
+        H, per, mi = codes.config_matrix(name)
+        dec = pkg.BeliefPropagationDecoder(H, per, mi)
+        info = dec.info()
+        dec.close()
+        assert info["family"] == fam, (name, info)
+        if fam == SMEM:
+            assert info["ctas_per_sm"] == 2, info
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 95, 1000])
+@pytest.mark.parametrize("fam", [SMEM, GLOBAL])
+def test_ragged_batches(pkg, oracle, codes, B, fam):
+    H, _, mi = codes.config_matrix("C3")
+    _, syn = oracle.sample(H, 0.06, 99, 1000, B)
+    ref = oracle.batch_decode(H, 0.06, mi, syn)
+    assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam), ref)
+
+
+@pytest.mark.parametrize("fam", [SMEM, GLOBAL])
+def test_semantic_edge_cases(pkg, oracle, codes, fam):
+    H, _, _ = codes.config_matrix("C3")
+    s, n = H.shape
+    zero = np.zeros((s, 40), dtype=np.uint8)
+    g = run_gpu(pkg, H, 0.01, 0, zero, family=fam)          # max_iters = 0
+    assert not g["errors"].any() and not g["converged"].any() and (g["iters"] == 0).all()
+    g = run_gpu(pkg, H, 0.01, 5, zero, family=fam)          # zero syndrome: converged at iteration 1
+    assert not g["errors"].any() and g["converged"].all() and (g["iters"] == 1).all()
+    for per in (0.5, 0.7, 0.999):                           # prior ratio >= 1, ties -> 1
+        _, syn = oracle.sample(H, 0.3, 5, 0, 64)
+        ref = oracle.batch_decode(H, per, 7, syn, want_ratio=True)
+        assert_same(run_gpu(pkg, H, per, 7, syn, family=fam, want_ratio=True), ref, want_ratio=True)
+    for mi in (1, 2, 3):                                    # non-converged outputs of iteration max_iters
+        _, syn = oracle.sample(H, 0.1, 6, 0, 200)
+        ref = oracle.batch_decode(H, 0.1, mi, syn, want_ratio=True)
+        assert_same(run_gpu(pkg, H, 0.1, mi, syn, family=fam, want_ratio=True), ref, want_ratio=True)
+
+
+@pytest.mark.parametrize("fam", [SMEM, GLOBAL])
+def test_irregular_and_degenerate_graphs(pkg, oracle, fam):
+    rng = np.random.default_rng(5)
+    # empty rows / columns, degree-1 nodes, one heavy row (local-memory degree path) and one heavy column
+    s, n = 40, 90
+    H = (rng.random((s, n)) < 0.06).astype(np.uint8)
+    H[3, :] = 0
+    H[:, 7] = 0
+    H[5, :] = 0
+    H[5, 10] = 1
+    H[9, 20:55] = 1          # check degree 35 > 12
+    H[10:30, 60] = 1         # variable degree >= 20 > 12
+    H = sp.csc_matrix(H)
+    for per in (0.02, 0.2):
+        e = (rng.random((n, 300)) < per).astype(np.uint8)
+        syn = np.asarray((H @ e) % 2).astype(np.uint8)
+        syn[3, ::7] = 1      # unsatisfiable empty check -> never converges
+        ref = oracle.batch_decode(H, per, 20, syn, want_ratio=True)
+        g = run_gpu(pkg, H, per, 20, syn, family=fam, want_ratio=True)
+        assert_same(g, ref, want_ratio=True)
+        assert not ref["converged"][::7].any()
+
+
+def test_tiny_codes(pkg, oracle):
+    for Hd in ([[1]], [[1, 1]], [[1, 1, 0], [0, 1, 1]], [[1, 1, 0, 0, 0], [0, 1, 1, 1, 0], [0, 0, 0, 1, 1]]):
+        H = sp.csc_matrix(np.array(Hd, dtype=np.uint8))
+        s, n = H.shape
+        syn = np.array([[(b >> i) & 1 for b in range(1 << s)] for i in range(s)], dtype=np.uint8)
+        for fam in (SMEM, GLOBAL):
+            ref = oracle.batch_decode(H, 0.1, 10, syn, want_ratio=True)
+            assert_same(run_gpu(pkg, H, 0.1, 10, syn, family=fam, want_ratio=True), ref, want_ratio=True)
+
+
+@pytest.mark.parametrize("fmt", ["u8", "i64", "bool"])
+def test_element_formats(pkg, oracle, codes, fmt):
+    H, _, mi = codes.config_matrix("C2")
+    _, syn = oracle.sample(H, 0.05, 31, 0, 777)
+    ref = oracle.batch_decode(H, 0.05, mi, syn)
+    assert_same(run_gpu(pkg, H, 0.05, mi, syn, fmt=fmt), ref)
+
+
+def test_bit_formats_and_packed_rows(pkg, oracle, codes):
+    """Julia BitMatrix chunks in and out (bit c*rows + r), and the native packed rows."""
+    lib = pkg._lib
+    for name in ("C3", "C2"):
+        H, _, mi = codes.config_matrix(name)
+        s, n = H.shape
+        B = 1237
+        _, syn = oracle.sample(H, 0.05, 8, 0, B)
+        ref = oracle.batch_decode(H, 0.05, mi, syn)
+        dec = pkg.BeliefPropagationDecoder(H, 0.05, mi, chunk=320)   # several chunks, word-aligned boundaries
+        # BitMatrix: column-major bit stream, 64-bit chunks
+        bits_in = np.packbits(syn.T.reshape(-1), bitorder="little")
+        bits_in = np.concatenate([bits_in, np.zeros((-len(bits_in)) % 8, dtype=np.uint8)])
+        out = np.zeros(((B * n + 63) // 64) * 8, dtype=np.uint8)
+        conv = np.zeros(B, dtype=np.uint8)
+        dec.decode_raw(B, bits_in, lib.FMT_BITS, 0, out, lib.FMT_BITS, 0, conv)
+        got = np.unpackbits(out, bitorder="little")[: B * n].reshape(B, n).T
+        assert np.array_equal(got, ref["errors"]) and np.array_equal(conv.astype(bool), ref["converged"])
+        # packed rows
+        SW, NW = (s + 31) // 32, (n + 31) // 32
+        pin = np.zeros((B, SW * 32), dtype=np.uint8)
+        pin[:, :s] = syn.T
+        pin = np.packbits(pin, axis=1, bitorder="little").view(np.uint32).copy()
+        pout = np.zeros((B, NW), dtype=np.uint32)
+        dec.decode_raw(B, pin, lib.FMT_PACKED32, 0, pout, lib.FMT_PACKED32, 0, conv)
+        got = np.unpackbits(pout.view(np.uint8), axis=1, bitorder="little")[:, :n].T
+        assert np.array_equal(got, ref["errors"])
+        # mixed: Matrix{Int} in, BitMatrix out (test_bp_decoder.jl:24-26)
+        out[:] = 0
+        dec.decode_raw(B, np.asfortranarray(syn.astype(np.int64)), lib.FMT_I64, s, out, lib.FMT_BITS, 0, conv)
+        got = np.unpackbits(out, bitorder="little")[: B * n].reshape(B, n).T
+        assert np.array_equal(got, ref["errors"])
+        dec.close()
+
+
+def test_decode_b_single_syndrome_api(pkg, oracle, codes):
+    """decode!(decoder, syndrome): aliased Float64 scratch.err, converged flag, log_probabs."""
+    H, per, mi = codes.config_matrix("C1")
+    errs, syn = oracle.sample(H, per, 2024, 0, 5)
+    ref = oracle.batch_decode(H, per, mi, syn, want_ratio=True)
+    dec = pkg.BeliefPropagationDecoder(H, per, mi)
+    for b in range(5):
+        for s_in in (syn[:, b], syn[:, b].astype(np.int64), syn[:, b].astype(bool)):
+            guess, success = pkg.decode_b(dec, s_in)
+            assert guess is dec.scratch.err and guess.dtype == np.float64
+            assert np.array_equal(guess.astype(np.uint8), ref["errors"][:, b]) and success == bool(ref["converged"][b])
+            with np.errstate(all="ignore"):
+                np.testing.assert_array_equal(dec.scratch.log_probabs, np.log(1.0 / ref["ratio"][:, b]))
+    assert pkg.reset_b(dec) is dec and not dec.scratch.err.any()
+    # 3-argument batchdecode! allocates success (abstract_decoder.jl:44-48); column-count asserts
+    errors = np.zeros((H.shape[1], 5), dtype=np.bool_, order="F")
+    out, success = pkg.batchdecode_b(dec, syn.astype(np.int64), errors)
+    assert out is errors and success.dtype == np.bool_ and np.array_equal(errors.astype(np.uint8), ref["errors"])
+    with pytest.raises(AssertionError):
+        pkg.batchdecode_b(dec, syn, np.zeros((H.shape[1], 4), dtype=np.uint8, order="F"))
+    with pytest.raises(AssertionError):
+        pkg.batchdecode_b(dec, syn, errors, np.zeros(3, dtype=np.bool_))
+    dec.close()
+
+
+def test_reference_thresholds_on_gpu(pkg, oracle, codes):
+    """test/test_bp_decoder.jl:46-51 against the GPU path."""
+    H = codes.gallager(1000, 10, 9, seed=7)
+    errs, syn = oracle.sample(H, 0.01, 4242, 0, 1100)
+    g = run_gpu(pkg, H, 0.01, 100, syn)
+    exact = (g["errors"] == errs).all(axis=0)
+    assert exact[0]
+    assert 1 - exact[:100].mean() < 0.005
+    assert 1 - exact[100:].mean() < 0.001
+
+
+def test_device_sampler_matches_oracle_and_full_size_properties(pkg, oracle, codes):
+    """Device-resident sample -> decode -> score on the gross code at 2M syndromes: the sampler
+    equals the oracle's Philox stream, every converged output reproduces its syndrome, counters
+    agree with per-syndrome outputs, and results do not depend on how the batch is split."""
+    H, _, mi = codes.config_matrix("C3")
+    s, n = H.shape
+    per = 0.03
+    dec = pkg.BeliefPropagationDecoder(H, per, mi)
+    info = dec.info()
+    SW, NW = info["syn_words"], info["err_words"]
+    B = 2_000_000
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
+    errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    conv = torch.empty(B, dtype=torch.uint8, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+    score = torch.zeros(2, dtype=torch.int64, device=dev)
+    dec.sample_device(B, 0, 12345, per, truth.data_ptr(), synw.data_ptr(), stream=st)
+    dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), None, ctr.data_ptr(), stream=st)
+    dec.score_device(B, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), score.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    # sampler == oracle stream on a prefix and in the middle (sharding independence)
+    for first, cnt in ((0, 500), (1_234_567, 300)):
+        e_ref, s_ref = oracle.sample(H, per, 12345, first, cnt)
+        e_gpu = np.unpackbits(truth[first:first + cnt].cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, :n].T
+        s_gpu = np.unpackbits(synw[first:first + cnt].cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, :s].T
+        assert np.array_equal(e_gpu, e_ref) and np.array_equal(s_gpu, s_ref)
+        ref = oracle.batch_decode(H, per, mi, s_ref)
+        d_gpu = np.unpackbits(errw[first:first + cnt].cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, :n].T
+        assert np.array_equal(d_gpu, ref["errors"])
+        assert np.array_equal(conv[first:first + cnt].cpu().numpy().astype(bool), ref["converged"])
+        assert np.array_equal(iters[first:first + cnt].cpu().numpy(), ref["iters"])
+    c = ctr.cpu().numpy()
+    assert c[0] == B and c[1] == int(conv.sum().item()) and c[2] == int(iters.sum(dtype=torch.int64).item())
+    sc = score.cpu().numpy()
+    assert sc[1] == c[1]                     # converged <=> H*e == syndrome, over the whole batch
+    assert sc[0] <= sc[1] and sc[0] > 0.5 * B
+    assert int(iters.min().item()) >= 1 and int(iters.max().item()) <= mi
+    assert bool(((iters == mi) | (conv == 1)).all().item())
+    # a different split of the same batch gives the same bits
+    errw2 = torch.empty_like(errw[:700_000])
+    conv2 = torch.empty_like(conv[:700_000])
+    dec.decode_device(700_000, synw[300_000:].data_ptr(), errw2.data_ptr(), conv2.data_ptr(), None, None, None, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(errw2, errw[300_000:1_000_000]) and torch.equal(conv2, conv[300_000:1_000_000])
+    assert dec.launch_count() > 0
+    dec.close()
+
+
+def test_forced_iterations_mode_runs_max_iters(pkg, oracle, codes):
+    H, _, mi = codes.config_matrix("C3")
+    _, syn = oracle.sample(H, 0.01, 3, 0, 500)
+    g = run_gpu(pkg, H, 0.01, mi, syn, early_stop=0)
+    assert (g["iters"] == mi).all()
