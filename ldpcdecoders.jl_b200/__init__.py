@@ -4,7 +4,7 @@ Only the hot path of /root/reference/src/decoders/belief_propagation.jl is imple
 csrc/ holds the CUDA kernels and the C ABI (include/ldpcb200.h); decoder.py mirrors the
 reference's decoder interface on top of that ABI; codes.py builds the benchmark matrices.
 """
-from . import _lib, codes                                              # noqa: F401
+from . import _lib, codes, sharding                                              # noqa: F401
 from .decoder import (BeliefPropagationDecoder, BeliefPropagationScratchSpace,   # noqa: F401
                       decode_b, batchdecode_b, reset_b)
 
