@@ -226,8 +226,12 @@ def main():
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], **opts)
     info = dec.info()
     SW, NW = info["syn_words"], info["err_words"]
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: its handle is non-NULL, so the library launches on exactly the
+    # stream the torch CUDA events are recorded on (NULL would mean "the handle's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     st = stream.cuda_stream
+    assert st != 0
 
     def barrier():
         torch.cuda.synchronize()

@@ -134,6 +134,13 @@ int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
                           const uint32_t *d_true_err_words, const uint32_t *d_err_words,
                           const uint32_t *d_syn_words, unsigned long long *d_out, void *stream);
 
+/* Self-test of the kernels' branch-free division sequences against the stock IEEE routines
+ * (__drcp_rn / __ddiv_rn) on n pseudo-random operands of envelope `mode` (0: t = 2/(1+q)-1,
+ * 1: r = (1-x)/(1+x)).  mismatches[4]: [0] node map vs stock IEEE form, [1] refined reciprocal vs
+ * __drcp_rn, [2] __drcp_rn vs __ddiv_rn(1,d), [3] bits of one offending operand; [0..2] must come
+ * back 0.  Test hook, not part of the decode path. */
+int ldpcb200_selftest_division(int32_t device, int32_t mode, uint64_t n, uint64_t seed, uint64_t *mismatches);
+
 /* Number of kernels of this library launched through the handle so far (bench bookkeeping). */
 int ldpcb200_launch_count(const ldpcb200_t *h, int64_t *out);
 

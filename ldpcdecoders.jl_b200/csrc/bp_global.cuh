@@ -130,8 +130,6 @@ __global__ void __launch_bounds__(256) bp_global_var(const __grid_constant__ Glo
 __global__ void __launch_bounds__(256) bp_global_finish(const __grid_constant__ GlobalParams p, int first)
 {
     __shared__ long long s_base;
-    __shared__ long long s_sid[32];
-    __shared__ int s_done[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int slab = blockIdx.x;
     const int slot = slab * 32 + lane;
@@ -150,10 +148,6 @@ __global__ void __launch_bounds__(256) bp_global_finish(const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         s_base = ndone ? static_cast<long long>(atomicAdd(p.queue, static_cast<unsigned long long>(ndone))) : 0;
-    }
-    if (warp == 0) {
-        s_sid[lane] = old_sid;
-        s_done[lane] = done ? 1 : 0;
     }
     __syncthreads();
     long long new_sid = -1;

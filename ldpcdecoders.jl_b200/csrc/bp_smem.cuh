@@ -42,9 +42,9 @@ struct SmemParams {
     int32_t *iters;               // [B] or null
     double *ratio;                // [B][n] or null
     unsigned long long *counters; // [4] or null
-    const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve u32[E]
+    const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | ve_chk u16[E]
     int tables_bytes;             // multiple of 16
-    int off_colptr, off_ve;       // byte offsets inside the blob (rowptr at 0)
+    int off_colptr, off_ve, off_vchk;   // byte offsets inside the blob (rowptr at 0)
     // shared-memory carve-up (byte offsets from the dynamic smem base)
     int off_syn, off_resid, off_errb, off_stage, off_nnz, off_tables, off_mbar;
 };
@@ -89,11 +89,11 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool BIG>
-__global__ void __launch_bounds__(512, 1) bp_smem_kernel(const __grid_constant__ SmemParams p)
+// MAXT / MINB: launch bounds (two instantiations: 2 CTAs/SM with up to 384 threads, 1 CTA/SM with 512)
+template <bool BIG, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_constant__ SmemParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    double *msg = reinterpret_cast<double *>(smem);
     uint32_t *syn = reinterpret_cast<uint32_t *>(smem + p.off_syn);
     uint32_t *resid = reinterpret_cast<uint32_t *>(smem + p.off_resid);
     uint32_t *errb = reinterpret_cast<uint32_t *>(smem + p.off_errb);
@@ -101,13 +101,15 @@ __global__ void __launch_bounds__(512, 1) bp_smem_kernel(const __grid_constant__
     int *nnz = reinterpret_cast<int *>(smem + p.off_nnz);          // [2][32]
     const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(smem + p.off_tables);
     const uint16_t *colptr = reinterpret_cast<const uint16_t *>(smem + p.off_tables + p.off_colptr);
-    const uint32_t *ve = reinterpret_cast<const uint32_t *>(smem + p.off_tables + p.off_ve);
+    const uint32_t *ve = reinterpret_cast<const uint32_t *>(smem + p.off_tables + p.off_ve);       // byte offset of the edge's slot row
+    const uint16_t *vchk = reinterpret_cast<const uint16_t *>(smem + p.off_tables + p.off_vchk);   // check of the edge
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned char *msgb = smem + lane * 8;         // this lane's column of the message array
 
     if (threadIdx.x == 0)
         tma_load_tables(smem + p.off_tables, p.tables, static_cast<uint32_t>(p.tables_bytes), mbar);
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(512, 1) bp_smem_kernel(const __grid_constant__
                 const int rp = rowptr[i];
                 const int deg = rowptr[i + 1] - rp;
                 const bool neg = (syn[(i >> 5) * 32 + lane] >> (i & 31)) & 1u;
-                double *base = msg + rp * 32 + lane;
+                double *base = reinterpret_cast<double *>(msgb + rp * 256);
 #define BP_CASE(D)                                                                   \
     {                                                                                \
         double m[D];                                                                 \
@@ -203,14 +205,14 @@ __global__ void __launch_bounds__(512, 1) bp_smem_kernel(const __grid_constant__
         uint32_t v[D];                                                               \
         double m[D];                                                                 \
         _Pragma("unroll") for (int k = 0; k < D; ++k) v[k] = ve[cp + k];             \
-        _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = msg[(v[k] & 0xffffu) * 32 + lane]; \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = *reinterpret_cast<double *>(msgb + v[k]); \
         R = var_update<D>(m, p.p0);                                                  \
-        _Pragma("unroll") for (int k = 0; k < D; ++k) msg[(v[k] & 0xffffu) * 32 + lane] = m[k]; \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) *reinterpret_cast<double *>(msgb + v[k]) = m[k]; \
     }
                 BP_DEGREE_SWITCH(
                     deg, BP_CASE, if (BIG) {
                         R = var_update_big(
-                            [&](int k) -> double & { return msg[(ve[cp + k] & 0xffffu) * 32 + lane]; }, deg, p.p0);
+                            [&](int k) -> double & { return *reinterpret_cast<double *>(msgb + ve[cp + k]); }, deg, p.p0);
                     })
 #undef BP_CASE
                 if (p.ratio) p.ratio[sid * p.n + j] = R;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(512, 1) bp_smem_kernel(const __grid_constant__
                     atomicXor(ew, 1u << (j & 31));
                     int delta = 0;
                     for (int k = 0; k < deg; ++k) {
-                        const uint32_t chk = ve[cp + k] >> 16;
+                        const uint32_t chk = vchk[cp + k];
                         const uint32_t bit = 1u << (chk & 31);
                         const uint32_t old = atomicXor(resid + (chk >> 5) * 32 + lane, bit);
                         delta += (old & bit) ? -1 : 1;

@@ -96,13 +96,14 @@ struct ldpcb200 {
     int SW = 0, NW = 0;
     std::vector<int> rowptr, colptr, ve_slot, ve_chk;
     std::vector<unsigned char> tables;   // SMEM-family blob
-    int off_colptr = 0, off_ve = 0;
+    int off_colptr = 0, off_ve = 0, off_vchk = 0;
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
     // resolved configuration
     bool configured = false;
     int family = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0;
+    bool two_ctas = false;
     bp::SmemParams sp_proto{};
     std::vector<DeviceCtx> dev;
     std::atomic<long long> launches{0};
@@ -170,21 +171,26 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
     h->NW = static_cast<int>((n + 31) / 32);
     if (h->SW == 0) h->SW = 1;
     if (h->NW == 0) h->NW = 1;
-    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve u32[E] (slot | chk << 16)
+    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes) | ve_chk u16[E]
     if (E <= 0xffff && s <= 0xffff && n <= 0xffff) {
         const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
         const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
-        const int total = align_up(o_ve + static_cast<int>(4 * E), 16);
+        const int o_chk = o_ve + static_cast<int>(4 * E);
+        const int total = align_up(o_chk + static_cast<int>(2 * E), 16);
         h->tables.assign(std::max(total, 16), 0);
         uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
         uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
         uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
+        uint16_t *vc = reinterpret_cast<uint16_t *>(h->tables.data() + o_chk);
         for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->rowptr[i]);
         for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->colptr[j]);
-        for (int64_t e = 0; e < E; ++e)
-            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) | (static_cast<uint32_t>(h->ve_chk[e]) << 16);
+        for (int64_t e = 0; e < E; ++e) {
+            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
+            vc[e] = static_cast<uint16_t>(h->ve_chk[e]);
+        }
         h->off_colptr = o_col;
         h->off_ve = o_ve;
+        h->off_vchk = o_chk;
     }
     return 0;
 }
@@ -233,14 +239,40 @@ void destroy_device(DeviceCtx &d)
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
-template <bool BIG>
+template <bool BIG, int MAXT, int MINB>
 int smem_kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
 {
-    CU(cudaFuncSetAttribute(bp::bp_smem_kernel<BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CU(cudaFuncSetAttribute(bp::bp_smem_kernel<BIG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bp::bp_smem_kernel<BIG>, threads, smem_bytes));
+    auto k = bp::bp_smem_kernel<BIG, MAXT, MINB>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes));
     return 0;
+}
+
+// Instantiations of the persistent kernel: (threads <= 256, 2 CTAs/SM, <=128 regs),
+// (threads <= 384, 2 CTAs/SM, <=80 regs), (threads <= 512, 1 CTA/SM).
+enum SmemShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
+
+int smem_shape(bool two_ctas, int threads) { return !two_ctas ? kShape512x1 : (threads <= 256 ? kShape256x2 : kShape384x2); }
+
+template <bool BIG>
+int smem_attrs_for(int shape, int smem_bytes, int threads, int *bps)
+{
+    switch (shape) {
+        case kShape256x2: return smem_kernel_attrs<BIG, 256, 2>(smem_bytes, threads, bps);
+        case kShape384x2: return smem_kernel_attrs<BIG, 384, 2>(smem_bytes, threads, bps);
+        default: return smem_kernel_attrs<BIG, 512, 1>(smem_bytes, threads, bps);
+    }
+}
+
+template <bool BIG>
+void smem_launch_for(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const bp::SmemParams &p)
+{
+    switch (shape) {
+        case kShape256x2: bp::bp_smem_kernel<BIG, 256, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        case kShape384x2: bp::bp_smem_kernel<BIG, 384, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        default: bp::bp_smem_kernel<BIG, 512, 1><<<grid, threads, smem_bytes, st>>>(p); break;
+    }
 }
 
 // Resolve family / launch shape from the code size, the options and device 0's limits.
@@ -260,12 +292,14 @@ int configure(ldpcb200 *h)
     h->family = family;
     if (family == LDPCB200_FAMILY_SMEM) {
         const bool two = 2 * (need + 1024) <= d0.smem_per_sm;
-        int warps = h->opt_warps > 0 ? h->opt_warps : (two ? 8 : 16);
-        warps = std::max(1, std::min(16, warps));
+        int warps = h->opt_warps > 0 ? h->opt_warps : (two ? 12 : 16);
+        warps = std::max(1, std::min(two ? 12 : 16, warps));
+        h->two_ctas = two;
+        const int shape = smem_shape(two, warps * 32);
         int bps = 0, rc;
         for (DeviceCtx &d : h->dev) {
             CU(cudaSetDevice(d.device));
-            rc = h->big ? smem_kernel_attrs<true>(need, warps * 32, &bps) : smem_kernel_attrs<false>(need, warps * 32, &bps);
+            rc = h->big ? smem_attrs_for<true>(shape, need, warps * 32, &bps) : smem_attrs_for<false>(shape, need, warps * 32, &bps);
             if (rc) return rc;
         }
         if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "family SMEM kernel does not fit on an SM");
@@ -340,13 +374,12 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
         p.counters = counters;
         p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
-        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve;
+        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vchk = h->off_vchk;
         const long long nchunks = (B + 31) / 32;
         const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
-        if (h->big)
-            bp::bp_smem_kernel<true><<<grid, h->warps * 32, h->smem_bytes, st>>>(p);
-        else
-            bp::bp_smem_kernel<false><<<grid, h->warps * 32, h->smem_bytes, st>>>(p);
+        const int thr = h->warps * 32;
+        if (h->big) smem_launch_for<true>(smem_shape(h->two_ctas, thr), grid, thr, h->smem_bytes, st, p);
+        else smem_launch_for<false>(smem_shape(h->two_ctas, thr), grid, thr, h->smem_bytes, st, p);
         h->launches++;
         CU(cudaGetLastError());
         return 0;
@@ -722,6 +755,22 @@ int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint
                                                                 d.scratch.as<uint32_t>(), d_out);
     h->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int ldpcb200_selftest_division(int32_t device, int32_t mode, uint64_t n, uint64_t seed, uint64_t *mismatches)
+{
+    if (!mismatches || (mode != 0 && mode != 1)) return fail(LDPCB200_EINVAL, "bad selftest arguments");
+    CU(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, 32));
+    CU(cudaMemset(d, 0, 32));
+    bp::selftest_division<<<148 * 8, 256>>>(mode, n, seed, d);
+    unsigned long long hcount[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpy(hcount, d, 32, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "selftest: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 4; ++k) mismatches[k] = hcount[k];
     return 0;
 }
 

@@ -242,7 +242,9 @@ def test_device_sampler_matches_oracle_and_full_size_properties(pkg, oracle, cod
     SW, NW = info["syn_words"], info["err_words"]
     B = 2_000_000
     dev = torch.device("cuda:0")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
     synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
     errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
@@ -280,6 +282,18 @@ def test_device_sampler_matches_oracle_and_full_size_properties(pkg, oracle, cod
     assert torch.equal(errw2, errw[300_000:1_000_000]) and torch.equal(conv2, conv[300_000:1_000_000])
     assert dec.launch_count() > 0
     dec.close()
+
+
+def test_fast_division_is_ieee(pkg):
+    """The kernels' branch-free reciprocal / quotient sequences equal __drcp_rn / __ddiv_rn bit for
+    bit on their operand envelopes (2^31 pseudo-random operands each, incl. values next to the
+    envelope edges)."""
+    import ctypes
+    lib = pkg._lib.load()
+    for mode in (0, 1):
+        bad = (ctypes.c_uint64 * 4)(1, 1, 1, 1)
+        pkg._lib.check(lib.ldpcb200_selftest_division(0, mode, 1 << 31, 2024 + mode, bad))
+        assert list(bad)[:3] == [0, 0, 0], (mode, list(bad), np.array([bad[3]], dtype=np.uint64).view(np.float64))
 
 
 def test_forced_iterations_mode_runs_max_iters(pkg, oracle, codes):
