@@ -22,6 +22,7 @@ struct GlobalParams {
     int max_iters, early_stop;
     int nslab;
     double p0;
+    int regular_p0;
     long long B;
     const uint32_t *syn_words;
     uint32_t *err_words;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) bp_global_var(const __grid_constant__ Glo
         double m[D];                                                                 \
         _Pragma("unroll") for (int k = 0; k < D; ++k) v[k] = p.ve_slot[cp + k];      \
         _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = mb[static_cast<size_t>(v[k]) * 32]; \
-        R = var_update<D>(m, p.p0);                                                  \
+        R = var_update<D>(m, p.p0, p.regular_p0 != 0);                                                  \
         _Pragma("unroll") for (int k = 0; k < D; ++k) mb[static_cast<size_t>(v[k]) * 32] = m[k]; \
     }
         BP_DEGREE_SWITCH(

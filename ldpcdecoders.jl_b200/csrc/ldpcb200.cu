@@ -90,13 +90,15 @@ struct DeviceCtx {
 struct ldpcb200 {
     int64_t s = 0, n = 0, E = 0;
     double per = 0, p0 = 0;
+    int regular_p0 = 0;
     int max_iters = 0, variant = 0;
     int max_cdeg = 0, max_vdeg = 0;
+    int uni_cdeg = 0, uni_vdeg = 0;   // common degree when every check / variable has the same one (<= 12)
     bool big = false;
     int SW = 0, NW = 0;
     std::vector<int> rowptr, colptr, ve_slot, ve_chk;
     std::vector<unsigned char> tables;   // SMEM-family blob
-    int off_colptr = 0, off_ve = 0, off_vchk = 0;
+    int off_colptr = 0, off_ve = 0;
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
@@ -119,7 +121,6 @@ int smem_layout(const ldpcb200 *h, bp::SmemParams &p)
     int off = static_cast<int>(h->E) * 32 * 8;
     p.off_syn = off;    off += h->SW * 128;
     p.off_resid = off;  off += h->SW * 128;
-    p.off_errb = off;   off += h->NW * 128;
     p.off_stage = off;  off += h->SW * 128;
     p.off_nnz = off;    off += 2 * 32 * 4;
     off = align_up(off, 16);
@@ -167,30 +168,31 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
         return fail(LDPCB200_EUNSUPPORTED, "node degree %d exceeds LDPCB200_MAX_DEGREE=%d",
                     std::max(h->max_cdeg, h->max_vdeg), LDPCB200_MAX_DEGREE);
     h->big = std::max(h->max_cdeg, h->max_vdeg) > bp::kMaxRegDegree;
+    {
+        bool uc = s > 0, uv = n > 0;
+        for (int64_t i = 0; i < s; ++i) uc &= (h->rowptr[i + 1] - h->rowptr[i]) == h->max_cdeg;
+        for (int64_t j = 0; j < n; ++j) uv &= (h->colptr[j + 1] - h->colptr[j]) == h->max_vdeg;
+        h->uni_cdeg = (uc && h->max_cdeg >= 1 && h->max_cdeg <= bp::kMaxRegDegree) ? h->max_cdeg : 0;
+        h->uni_vdeg = (uv && h->max_vdeg >= 1 && h->max_vdeg <= bp::kMaxRegDegree) ? h->max_vdeg : 0;
+    }
     h->SW = static_cast<int>((s + 31) / 32);
     h->NW = static_cast<int>((n + 31) / 32);
     if (h->SW == 0) h->SW = 1;
     if (h->NW == 0) h->NW = 1;
-    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes) | ve_chk u16[E]
+    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes)
     if (E <= 0xffff && s <= 0xffff && n <= 0xffff) {
         const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
         const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
-        const int o_chk = o_ve + static_cast<int>(4 * E);
-        const int total = align_up(o_chk + static_cast<int>(2 * E), 16);
+        const int total = align_up(o_ve + static_cast<int>(4 * E), 16);
         h->tables.assign(std::max(total, 16), 0);
         uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
         uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
         uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
-        uint16_t *vc = reinterpret_cast<uint16_t *>(h->tables.data() + o_chk);
         for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->rowptr[i]);
         for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->colptr[j]);
-        for (int64_t e = 0; e < E; ++e) {
-            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
-            vc[e] = static_cast<uint16_t>(h->ve_chk[e]);
-        }
+        for (int64_t e = 0; e < E; ++e) ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
         h->off_colptr = o_col;
         h->off_ve = o_ve;
-        h->off_vchk = o_chk;
     }
     return 0;
 }
@@ -250,16 +252,37 @@ int smem_kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
 }
 
 // Instantiations of the persistent kernel: (threads <= 256, 2 CTAs/SM, <=128 regs),
-// (threads <= 384, 2 CTAs/SM, <=80 regs), (threads <= 512, 1 CTA/SM).
-enum SmemShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
+// (<= 320, 2 CTAs/SM, <= 96 regs), (<= 384, 2 CTAs/SM, <= 80 regs), (<= 512, 1 CTA/SM).
+enum SmemShape { kShape256x2 = 0, kShape320x2 = 1, kShape384x2 = 2, kShape512x1 = 3 };
 
-int smem_shape(bool two_ctas, int threads) { return !two_ctas ? kShape512x1 : (threads <= 256 ? kShape256x2 : kShape384x2); }
+int smem_shape(bool two_ctas, int threads)
+{
+    if (!two_ctas) return kShape512x1;
+    return threads <= 256 ? kShape256x2 : (threads <= 320 ? kShape320x2 : kShape384x2);
+}
+
+// Warps per CTA: warp w owns checks w, w+W, ... and variables w, w+W, ...; pick the W
+// whose two round-robin splits waste the fewest warp-slots (ties -> more warps, better latency hiding).
+int pick_warps(int64_t s, int64_t n, int wmax)
+{
+    double best = -1.0;
+    int best_w = wmax;
+    for (int w = 4; w <= wmax; ++w) {
+        if ((n + w - 1) / w > 64) continue;      // decision bit field of a warp is one 64-bit register
+        const double ec = s > 0 ? static_cast<double>(s) / (w * ((s + w - 1) / w)) : 1.0;
+        const double ev = n > 0 ? static_cast<double>(n) / (w * ((n + w - 1) / w)) : 1.0;
+        const double score = 0.6 * ec + 0.4 * ev + 0.004 * w;
+        if (score > best) { best = score; best_w = w; }
+    }
+    return best_w;
+}
 
 template <bool BIG>
 int smem_attrs_for(int shape, int smem_bytes, int threads, int *bps)
 {
     switch (shape) {
         case kShape256x2: return smem_kernel_attrs<BIG, 256, 2>(smem_bytes, threads, bps);
+        case kShape320x2: return smem_kernel_attrs<BIG, 320, 2>(smem_bytes, threads, bps);
         case kShape384x2: return smem_kernel_attrs<BIG, 384, 2>(smem_bytes, threads, bps);
         default: return smem_kernel_attrs<BIG, 512, 1>(smem_bytes, threads, bps);
     }
@@ -270,6 +293,7 @@ void smem_launch_for(int shape, int grid, int threads, int smem_bytes, cudaStrea
 {
     switch (shape) {
         case kShape256x2: bp::bp_smem_kernel<BIG, 256, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        case kShape320x2: bp::bp_smem_kernel<BIG, 320, 2><<<grid, threads, smem_bytes, st>>>(p); break;
         case kShape384x2: bp::bp_smem_kernel<BIG, 384, 2><<<grid, threads, smem_bytes, st>>>(p); break;
         default: bp::bp_smem_kernel<BIG, 512, 1><<<grid, threads, smem_bytes, st>>>(p); break;
     }
@@ -292,8 +316,10 @@ int configure(ldpcb200 *h)
     h->family = family;
     if (family == LDPCB200_FAMILY_SMEM) {
         const bool two = 2 * (need + 1024) <= d0.smem_per_sm;
-        int warps = h->opt_warps > 0 ? h->opt_warps : (two ? 12 : 16);
+        int warps = h->opt_warps > 0 ? h->opt_warps : pick_warps(h->s, h->n, two ? 12 : 16);
         warps = std::max(1, std::min(two ? 12 : 16, warps));
+        if ((h->n + warps - 1) / warps > 64)
+            return fail(LDPCB200_EUNSUPPORTED, "family SMEM needs ceil(n / warps) <= 64 (n = %lld, warps = %d)", (long long)h->n, warps);
         h->two_ctas = two;
         const int shape = smem_shape(two, warps * 32);
         int bps = 0, rc;
@@ -369,12 +395,15 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     if (h->family == LDPCB200_FAMILY_SMEM) {
         bp::SmemParams p = h->sp_proto;
         p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
-        p.SW = h->SW; p.NW = h->NW;
+        p.SW = h->SW; p.NW = h->NW; p.uni_cdeg = h->uni_cdeg; p.uni_vdeg = h->uni_vdeg;
         p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop; p.p0 = h->p0; p.B = B;
+        p.regular_p0 = h->regular_p0;
         p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
         p.counters = counters;
         p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
-        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vchk = h->off_vchk;
+        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.vchk = d.d_ve_chk;
+        // finished lanes OR their set decision bits into the row: rows start out zero
+        CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
         const long long nchunks = (B + 31) / 32;
         const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
         const int thr = h->warps * 32;
@@ -391,7 +420,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     bp::GlobalParams p{};
     p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
     p.SW = h->SW; p.NW = h->NW; p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop;
-    p.nslab = nslab; p.p0 = h->p0; p.B = B;
+    p.nslab = nslab; p.p0 = h->p0; p.B = B; p.regular_p0 = h->regular_p0;
     p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
     p.counters = counters;
     p.rowptr = d.d_rowptr; p.colptr = d.d_colptr; p.ve_slot = d.d_ve_slot; p.ve_chk = d.d_ve_chk;
@@ -598,6 +627,7 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
         volatile double one_minus = 1.0 - per;
         volatile double q = per / one_minus;
         h->p0 = q;
+        h->regular_p0 = std::isnormal(h->p0) && h->p0 > 0.0;
     }
     int rc = build_graph(h, colptr, rowval, index_base);
     if (rc) { delete h; return rc; }
