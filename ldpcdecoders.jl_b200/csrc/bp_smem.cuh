@@ -46,10 +46,9 @@ struct SmemParams {
     int32_t *iters;               // [B] or null
     double *ratio;                // [B][n] or null
     unsigned long long *counters; // [4] or null
-    const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E]
+    const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
     int tables_bytes;             // multiple of 16
-    int off_colptr, off_ve;       // byte offsets inside the blob (rowptr at 0)
-    const int *vchk;              // global [E]: check of CSC edge e (only read when a decision flips)
+    int off_colptr, off_ve, off_vflip;   // byte offsets inside the blob (rowptr at 0)
     // shared-memory carve-up (byte offsets from the dynamic smem base)
     int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar;
 };
@@ -188,7 +187,6 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     uint32_t *resid = reinterpret_cast<uint32_t *>(smem + p.off_resid);
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem + p.off_stage);
     int *nnz = reinterpret_cast<int *>(smem + p.off_nnz);          // [2][32]
-    const uint16_t *colptr = reinterpret_cast<const uint16_t *>(smem + p.off_tables + p.off_colptr);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
 
     const int lane = threadIdx.x & 31;
@@ -202,6 +200,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     const uint32_t rowptr_a = sbase + p.off_tables;
     const uint32_t colptr_a = sbase + p.off_tables + p.off_colptr;
     const uint32_t ve_a = sbase + p.off_tables + p.off_ve;         // u32 byte offset of each edge's slot row
+    const uint32_t vflip_a = sbase + p.off_tables + p.off_vflip;   // u16 residual word offset | bit of each edge's check
 
     if (threadIdx.x == 0)
         tma_load_tables(smem + p.off_tables, p.tables, static_cast<uint32_t>(p.tables_bytes), mbar);
@@ -345,11 +344,12 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
                 do {
                     const int j = warp + (__ffsll(static_cast<long long>(flips)) - 1) * W;
                     flips &= flips - 1;
-                    for (int e = colptr[j]; e < colptr[j + 1]; ++e) {
-                        const uint32_t chk = p.vchk[e];
-                        const uint32_t bit = 1u << (chk & 31);
-                        const uint32_t old = atomicXor(resid + (chk >> 5) * 32 + lane, bit);
-                        delta += (old & bit) ? -1 : 1;
+                    const int e1 = lds_u16(colptr_a + 2 * j + 2);
+                    for (int e = lds_u16(colptr_a + 2 * j); e < e1; ++e) {
+                        const uint32_t ent = lds_u16(vflip_a + 2 * e);        // (check/32)*128 + check%32
+                        const uint32_t old = atomicXor(reinterpret_cast<uint32_t *>(smem + p.off_resid + lane * 4 + (ent & 0xff80u)),
+                                                       1u << (ent & 31u));
+                        delta += 1 - 2 * static_cast<int>((old >> (ent & 31u)) & 1u);
                     }
                 } while (flips);
                 if (delta) atomicAdd(nnz + par * 32 + lane, delta);

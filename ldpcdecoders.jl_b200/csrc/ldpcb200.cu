@@ -98,7 +98,7 @@ struct ldpcb200 {
     int SW = 0, NW = 0;
     std::vector<int> rowptr, colptr, ve_slot, ve_chk;
     std::vector<unsigned char> tables;   // SMEM-family blob
-    int off_colptr = 0, off_ve = 0;
+    int off_colptr = 0, off_ve = 0, off_vflip = 0;
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
@@ -179,20 +179,27 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
     h->NW = static_cast<int>((n + 31) / 32);
     if (h->SW == 0) h->SW = 1;
     if (h->NW == 0) h->NW = 1;
-    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes)
-    if (E <= 0xffff && s <= 0xffff && n <= 0xffff) {
+    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes) | vflip u16[E]
+    if (E <= 0xffff && s <= 16384 && n <= 0xffff) {
         const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
         const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
-        const int total = align_up(o_ve + static_cast<int>(4 * E), 16);
+        const int o_fl = o_ve + static_cast<int>(4 * E);
+        const int total = align_up(o_fl + static_cast<int>(2 * E), 16);
         h->tables.assign(std::max(total, 16), 0);
         uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
         uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
         uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
         for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->rowptr[i]);
         for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->colptr[j]);
-        for (int64_t e = 0; e < E; ++e) ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
+        uint16_t *fl = reinterpret_cast<uint16_t *>(h->tables.data() + o_fl);
+        for (int64_t e = 0; e < E; ++e) {
+            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
+            // residual-syndrome word (byte offset of its 128 B row) | bit: needs s <= 16384
+            fl[e] = static_cast<uint16_t>((h->ve_chk[e] >> 5) * 128 + (h->ve_chk[e] & 31));
+        }
         h->off_colptr = o_col;
         h->off_ve = o_ve;
+        h->off_vflip = o_fl;
     }
     return 0;
 }
@@ -401,7 +408,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
         p.counters = counters;
         p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
-        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.vchk = d.d_ve_chk;
+        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
         // finished lanes OR their set decision bits into the row: rows start out zero
         CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
         const long long nchunks = (B + 31) / 32;
