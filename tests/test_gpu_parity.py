@@ -301,3 +301,18 @@ def test_forced_iterations_mode_runs_max_iters(pkg, oracle, codes):
     _, syn = oracle.sample(H, 0.01, 3, 0, 500)
     g = run_gpu(pkg, H, 0.01, mi, syn, early_stop=0)
     assert (g["iters"] == mi).all()
+
+
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("fixture", sorted(f for f in __import__("os").listdir(GOLDEN) if f.endswith(".npz")))
+def test_golden_fixtures_on_gpu(pkg, fixture):
+    """The committed fixtures (tests/golden/make_golden.py) decoded by the CUDA path."""
+    z = np.load(__import__("os").path.join(GOLDEN, fixture))
+    H = sp.csc_matrix((np.ones(len(z["rowval"]), dtype=np.uint8), z["rowval"], z["colptr"]), shape=tuple(z["shape"]))
+    g = run_gpu(pkg, H, float(z["per"]), int(z["max_iters"]), z["syndromes"], want_ratio=True)
+    assert np.array_equal(g["errors"], z["errors"])
+    assert np.array_equal(g["converged"], z["converged"])
+    assert np.array_equal(g["iters"], z["iters"])
+    assert np.array_equal(g["ratio"].view(np.uint64), z["ratio_bits"])
