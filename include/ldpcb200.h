@@ -49,8 +49,8 @@ typedef struct ldpcb200 ldpcb200_t;
 
 /* kernel families (ldpcb200_info_t.family, option "family") */
 #define LDPCB200_FAMILY_AUTO   0
-#define LDPCB200_FAMILY_SMEM   1  /* persistent, messages resident in shared memory, lane = syndrome */
-#define LDPCB200_FAMILY_GLOBAL 2  /* messages in HBM/L2, edge-major x syndrome-minor slabs */
+#define LDPCB200_FAMILY_SMEM   1  /* persistent kernel, messages resident in shared memory, lane = syndrome */
+#define LDPCB200_FAMILY_GLOBAL 2  /* same kernel, messages (and for very large codes state/tables) in HBM/L2 */
 
 typedef struct {
     int64_t s, n, E;            /* checks, variables, edges (nnz of H) */
@@ -61,9 +61,11 @@ typedef struct {
     int32_t ctas_per_sm;        /* family SMEM: resident CTAs per SM */
     int32_t threads_per_cta;
     int32_t smem_bytes;         /* dynamic shared memory per CTA (family SMEM) */
-    int32_t slots;              /* family GLOBAL: resident syndrome slots per device */
+    int32_t slots;              /* resident syndrome slots per device (32 x resident CTAs) */
     int32_t syn_words, err_words; /* uint32 words per packed syndrome / error row */
-    int64_t message_bytes;      /* device bytes of the message store per device */
+    int64_t message_bytes;      /* device bytes of the message store per device (family GLOBAL) */
+    int32_t kernel_mode;        /* 0: all in shared memory, 1: messages in HBM/L2, 2: messages + state + tables in HBM/L2 */
+    int32_t reserved_;
 } ldpcb200_info_t;
 
 /* counters[] layout of the decode calls (summed over all devices of the handle) */
@@ -90,7 +92,7 @@ int ldpcb200_destroy(ldpcb200_t *h);
 int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
 
 /* Tunables, set before the first decode (all optional):
- *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA, family SMEM), "slots" (family GLOBAL),
+ *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);

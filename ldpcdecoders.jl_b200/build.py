@@ -8,7 +8,7 @@ SRC_DIR = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libldpcb200.so")
 SOURCES = ["ldpcb200.cu"]
-HEADERS = ["bp_math.cuh", "bp_smem.cuh", "bp_global.cuh", "formats.cuh", "../../include/ldpcb200.h"]
+HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "formats.cuh", "../../include/ldpcb200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,516 @@
+// bp_kernel.cuh -- the persistent BP kernel: one launch runs every iteration of every syndrome.
+//
+// Replaces the whole of decode!/batchdecode! (/root/reference/src/decoders/belief_propagation.jl
+// :121-188, :220-231).
+//
+// Mapping
+//   CTA  = 32 "lanes" (syndrome slots) x W warps.  Lane l of EVERY warp works on the syndrome
+//          currently held in slot l; warp w owns checks w, w+W, ... in the check pass and
+//          variables w, w+W, ... in the variable pass.  All node indices are therefore
+//          warp-uniform (broadcast table reads, no divergence) and every message access is
+//          msg[slot_edge][lane]: 256 contiguous bytes per warp -- bank-conflict free in shared
+//          memory, fully coalesced in HBM.
+//   Messages: ONE in-place array per CTA, check-major edge order (a check's edges are
+//          contiguous); the check pass turns bit->check ratios into check->bit ratios in place,
+//          the variable pass turns them back.
+//   Where things live (template MODE):
+//          0  family SMEM  : messages, syndrome state and edge tables in shared memory
+//                            (surface d<=15, [[144,12,12]] gross code, ...; FP64-pipe bound)
+//          1  family GLOBAL: messages in HBM/L2 (E*256 B per CTA), state and tables in shared
+//                            memory (HGP-1600, Gallager n=1000, ...)
+//          2  family GLOBAL: messages, syndrome state and (32-bit) tables in HBM/L2
+//                            (Gallager n=100k: 77 MB of messages per CTA, HBM-bandwidth bound)
+//   Hard decisions and the syndrome re-check (belief_propagation.jl:164-168,180-184) are kept
+//          incrementally: each warp holds the decisions of its variables as a bit field in a
+//          register, resid = s xor H*e bit-packed, nnz = popcount(resid).  A variable whose
+//          decision flips XORs the bits of its checks in resid (atomics, lanes walk their own
+//          flips).  converged <=> nnz == 0.  A finished lane ORs its set bits into the
+//          pre-zeroed packed output row.
+//   Early termination / compaction: every lane has its own iteration counter.  A lane whose
+//          syndrome converged (or hit max_iters) writes its outputs and immediately takes the
+//          next syndrome of the CTA's queue, so no lane idles on finished syndromes.  Fresh
+//          lanes read the prior p/(1-p) instead of stored messages (initialisation :127-131
+//          without a store pass).
+//   Shared-memory edge tables are fetched with one TMA bulk copy (cp.async.bulk + mbarrier); the
+//          next 32 queued syndromes are prefetched with cp.async (modes 0/1).
+#pragma once
+#include <type_traits>
+
+#include "bp_math.cuh"
+
+namespace bp {
+
+struct KernelParams {
+    int s, n, E;
+    int uni_cdeg, uni_vdeg;   // common check / variable degree if the code is regular in it (1..12), else 0
+    int SW, NW;               // uint32 words per packed syndrome / error row
+    int max_iters;
+    int early_stop;           // 1 = reference semantics
+    double p0;                // per / (1 - per)
+    int regular_p0;           // p0 is a positive normal double (no NaN clamp can fire on finite messages)
+    long long B;
+    const uint32_t *syn_words;    // [B][SW]
+    uint32_t *err_words;          // [B][NW], zero on entry
+    uint8_t *conv;                // [B]
+    int32_t *iters;               // [B] or null
+    double *ratio;                // [B][n] or null
+    unsigned long long *counters; // [4] or null
+    // narrow tables (modes 0/1), copied to shared memory:
+    const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
+    int tables_bytes;             // multiple of 16
+    int off_colptr, off_ve, off_vflip;   // byte offsets inside the blob (rowptr at 0)
+    // wide tables (mode 2), read from global memory:
+    const int *g_rowptr, *g_colptr;      // [s+1], [n+1]
+    const uint32_t *g_ve_off;            // [E] slot * 256
+    const uint32_t *g_vflip;             // [E] (check/32)*128 + check%32
+    // global stores (modes 1/2): per CTA E*32 doubles of messages; mode 2 also 2*SW*32 words of state
+    double *msg_global;
+    uint32_t *state_global;
+    // decision bit fields when a warp owns more than 64 variables: nfw words per thread, laid out
+    // [word][thread]; in shared memory (off_efield) or, if efield_global != null, per CTA in HBM
+    int nfw;
+    uint32_t *efield_global;
+    // shared-memory carve-up (byte offsets from the dynamic smem base)
+    int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// One TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_tables(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(b)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+
+// ---- message / table accessors.  Shared-window handles are 32-bit shared-space addresses
+// computed once (no generic->shared conversions in the hot loops); global handles are pointers.
+template <int OFF = 0>
+__device__ __forceinline__ double ld_msg(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF = 0>
+__device__ __forceinline__ void st_msg(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF = 0>
+__device__ __forceinline__ double ld_msg(unsigned char *p) { return *reinterpret_cast<double *>(p + OFF); }
+template <int OFF = 0>
+__device__ __forceinline__ void st_msg(unsigned char *p, double v) { *reinterpret_cast<double *>(p + OFF) = v; }
+
+template <int OFF = 0>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+    return v;
+}
+// k-th slot offset of a variable: shared table (address) or global table (pointer)
+template <int K>
+__device__ __forceinline__ uint32_t ld_off(uint32_t vea) { return lds_u32<K * 4>(vea); }
+template <int K>
+__device__ __forceinline__ uint32_t ld_off(const uint32_t *vep) { return __ldg(vep + K); }
+
+template <int D, class MH, int K = 0>
+__device__ __forceinline__ void load_row(double (&m)[D], MH a)
+{
+    if constexpr (K < D) {
+        m[K] = ld_msg<K * 256>(a);
+        load_row<D, MH, K + 1>(m, a);
+    }
+}
+template <int D, class MH, int K = 0>
+__device__ __forceinline__ void store_row(const double (&m)[D], MH a)
+{
+    if constexpr (K < D) {
+        st_msg<K * 256>(a, m[K]);
+        store_row<D, MH, K + 1>(m, a);
+    }
+}
+template <int D, class TH, int K = 0>
+__device__ __forceinline__ void load_offsets(uint32_t (&v)[D], TH a)
+{
+    if constexpr (K < D) {
+        v[K] = ld_off<K>(a);
+        load_offsets<D, TH, K + 1>(v, a);
+    }
+}
+
+// One check node of degree D whose D message slots start at `a` (this lane's column,
+// consecutive slots 256 B apart).
+template <int D, class MH>
+__device__ __forceinline__ void check_node(MH a, bool neg, bool fresh, double p0)
+{
+    double m[D];
+    load_row<D>(m, a);
+    if (fresh) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) m[k] = p0;
+    }
+    check_update<D>(m, neg);
+    store_row<D>(m, a);
+}
+
+// One variable node of degree D; `vea` = handle of its D slot offsets, `ml` = this lane's
+// message column.  Returns the posterior ratio.
+template <int D, class MH, class TH>
+__device__ __forceinline__ double var_node(MH ml, TH vea, double p0, bool regular_p0)
+{
+    uint32_t v[D];
+    double m[D];
+    load_offsets<D>(v, vea);
+#pragma unroll
+    for (int k = 0; k < D; ++k) m[k] = ld_msg(ml + v[k]);
+    const double R = var_update<D>(m, p0, regular_p0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);
+    return R;
+}
+
+template <int MODE, bool BIG, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_constant__ KernelParams p)
+{
+    constexpr bool kMsgShared = MODE == 0;
+    constexpr bool kStateShared = MODE <= 1;
+    using MH = typename std::conditional<kMsgShared, uint32_t, unsigned char *>::type;   // message column handle
+    using TH = typename std::conditional<kStateShared, uint32_t, const uint32_t *>::type;  // slot-offset table handle
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase = smem_u32(smem);
+
+    // ---- where this CTA's data lives
+    MH ml;                                            // this lane's message column
+    unsigned char *msg_generic;                       // same, as a generic pointer (local-memory degree path)
+    if constexpr (kMsgShared) {
+        ml = sbase + lane * 8;
+        msg_generic = smem + lane * 8;
+    } else {
+        msg_generic = reinterpret_cast<unsigned char *>(p.msg_global + static_cast<size_t>(blockIdx.x) * p.E * 32) + lane * 8;
+        ml = msg_generic;
+    }
+    uint32_t *syn, *resid;                            // [SW][32] each
+    if constexpr (kStateShared) {
+        syn = reinterpret_cast<uint32_t *>(smem + p.off_syn);
+        resid = reinterpret_cast<uint32_t *>(smem + p.off_resid);
+    } else {
+        syn = p.state_global + static_cast<size_t>(blockIdx.x) * 2 * p.SW * 32;
+        resid = syn + static_cast<size_t>(p.SW) * 32;
+    }
+    // decision fields in memory (only when a warp owns more than 64 variables)
+    const bool use_regs = p.n <= 64 * W;
+    uint32_t *efield = p.efield_global ? p.efield_global + static_cast<size_t>(blockIdx.x) * p.nfw * blockDim.x + threadIdx.x
+                                       : reinterpret_cast<uint32_t *>(smem + p.off_efield) + threadIdx.x;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + p.off_stage);
+    int *nnz = reinterpret_cast<int *>(smem + p.off_nnz);          // [2][32]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
+    const uint32_t syn_a = sbase + p.off_syn + lane * 4;
+    const uint32_t rowptr_a = sbase + p.off_tables;
+    const uint32_t colptr_a = sbase + p.off_tables + p.off_colptr;
+    const uint32_t ve_a = sbase + p.off_tables + p.off_ve;         // u32 byte offset of each edge's slot row
+    const uint32_t vflip_a = sbase + p.off_tables + p.off_vflip;   // u16 residual word offset | bit of each edge's check
+
+    auto rowptr_at = [&](int i) -> int {
+        if constexpr (kStateShared) return static_cast<int>(lds_u16(rowptr_a + 2 * i));
+        else return __ldg(p.g_rowptr + i);
+    };
+    auto colptr_at = [&](int j) -> int {
+        if constexpr (kStateShared) return static_cast<int>(lds_u16(colptr_a + 2 * j));
+        else return __ldg(p.g_colptr + j);
+    };
+    auto vflip_at = [&](int e) -> uint32_t {
+        if constexpr (kStateShared) return lds_u16(vflip_a + 2 * e);
+        else return __ldg(p.g_vflip + e);
+    };
+    auto ve_handle = [&](int e) -> TH {               // handle of the slot offsets starting at edge e
+        if constexpr (kStateShared) return ve_a + 4 * e;
+        else return p.g_ve_off + e;
+    };
+    auto syn_bit = [&](int i) -> bool {
+        if constexpr (kStateShared) return (lds_u32(syn_a + (i >> 5) * 128) >> (i & 31)) & 1u;
+        else return (syn[(i >> 5) * 32 + lane] >> (i & 31)) & 1u;
+    };
+
+    if constexpr (kStateShared) {
+        if (threadIdx.x == 0)
+            tma_load_tables(smem + p.off_tables, p.tables, static_cast<uint32_t>(p.tables_bytes), mbar);
+    }
+
+    // This CTA's queue: 32-syndrome chunks c, c+G, c+2G, ... of the batch.
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long nchunks = (p.B + 31) >> 5;
+    const long long my_chunks = (c < nchunks) ? (nchunks - c + G - 1) / G : 0;
+    const long long Q = my_chunks << 5;
+    auto sid_of = [&](long long q) -> long long {
+        const long long sid = (((q >> 5) * G + c) << 5) + (q & 31);
+        return (q < Q && sid < p.B) ? sid : -1;
+    };
+    auto prefetch = [&](long long q_head) {      // warp 0: stage[w][r] <- syndrome words of entry q_head + r
+        if constexpr (kStateShared) {
+            const long long sid = sid_of(q_head + lane);
+            if (sid >= 0)
+                for (int w = 0; w < p.SW; ++w) cp_async4(&stage[w * 32 + lane], p.syn_words + sid * p.SW + w);
+        }
+    };
+
+    long long q_head = 0;
+    long long sid = -1;
+    int iter = 0;
+    bool active = false, fresh = false;
+    int par = 0;                                  // which nnz buffer the coming iteration updates
+    // Hard decisions of the variables this warp owns (j = warp + i*W  <->  bit i), one bit set per
+    // variable currently decided 1 (codes with at most 64 variables per warp; else `efield`).
+    unsigned long long ebits = 0;
+    unsigned long long n_done = 0, n_conv = 0, n_iters = 0;   // warp 0 only
+
+    if (warp == 0) prefetch(0);
+    __syncthreads();
+    if constexpr (kStateShared) mbar_wait(mbar, 0);           // tables have landed
+
+    // Lanes in `mask` take the next queue entries.  Executed identically by every warp
+    // (register state is replicated); warp 0 additionally moves the syndrome in.
+    auto refill = [&](uint32_t mask, int nnz_buf) {
+        if constexpr (kStateShared) {
+            if (warp == 0) { cp_async_wait_all(); __syncwarp(); }
+        }
+        if ((mask >> lane) & 1u) {
+            const int rank = __popc(mask & lt_mask);
+            sid = sid_of(q_head + rank);
+            active = sid >= 0;
+            fresh = active;
+            iter = 0;
+            ebits = 0;                                                      // err .= 0 (reset!, :89)
+            if (!use_regs)
+                for (int k = 0; k < p.nfw; ++k) efield[static_cast<size_t>(k) * blockDim.x] = 0u;
+            if (warp == 0 && active) {
+                int cnt = 0;
+                for (int w = 0; w < p.SW; ++w) {
+                    uint32_t v;
+                    if constexpr (kStateShared) v = stage[w * 32 + rank];
+                    else v = p.syn_words[sid * p.SW + w];
+                    syn[w * 32 + lane] = v;
+                    resid[w * 32 + lane] = v;
+                    cnt += __popc(v);
+                }
+                nnz[nnz_buf * 32 + lane] = cnt;
+            }
+        }
+        q_head += __popc(mask);
+        if constexpr (kStateShared) {
+            if (warp == 0) { __syncwarp(); prefetch(q_head); }
+        }
+    };
+
+    refill(0xffffffffu, par);
+    __syncthreads();
+
+    const double p0 = p.p0;
+    const bool regular_p0 = p.regular_p0;
+    while (__ballot_sync(0xffffffffu, active) != 0u) {
+        // ------------------------------------------------------------------ check pass (:135-150)
+        // warp w owns checks w, w+W, ...; syndrome bit of check i = bit i%32 of syn[i/32][lane]
+        if (active) {
+            if (p.uni_cdeg) {
+                // every check has the same degree: slots of check i start at i*D, no table reads
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        MH a = ml + warp * (D * 256);                                                            \
+        for (int i = warp; i < p.s; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit(i), fresh, p0); \
+    }
+                BP_DEGREE_SWITCH(p.uni_cdeg, BP_CASE, ;)
+#undef BP_CASE
+            } else {
+                for (int i = warp; i < p.s; i += W) {
+                    const int rp = rowptr_at(i);
+                    const int deg = rowptr_at(i + 1) - rp;
+                    const bool neg = syn_bit(i);
+                    const MH a = ml + rp * 256;
+#define BP_CASE(D) check_node<D>(a, neg, fresh, p0)
+                    BP_DEGREE_SWITCH(
+                        deg, BP_CASE, if (BIG) {
+                            double *base = reinterpret_cast<double *>(msg_generic + static_cast<size_t>(rp) * 256);
+                            check_update_big([&](int k) -> double & { return base[k * 32]; }, deg, neg, fresh, p0);
+                        })
+#undef BP_CASE
+                }
+            }
+        }
+        __syncthreads();
+        // --------------------------------------------------------------- variable pass (:152-178)
+        // warp w owns variables w, w+W, ...; decision of its i-th variable = bit i of newbits
+        if (active) {
+            unsigned long long newbits = 0;
+            unsigned long long flips = 0;
+            int delta = 0;
+            // a lane walks its flipped variables (bits of f, first bit = variable index ibase)
+            auto apply_flips = [&](unsigned long long f, int ibase) {
+                while (f) {
+                    const int j = warp + (ibase + __ffsll(static_cast<long long>(f)) - 1) * W;
+                    f &= f - 1;
+                    const int e1 = colptr_at(j + 1);
+                    for (int e = colptr_at(j); e < e1; ++e) {
+                        const uint32_t ent = vflip_at(e);                 // (check/32)*128 + check%32
+                        const uint32_t old = atomicXor(resid + (ent >> 7) * 32 + lane, 1u << (ent & 31u));
+                        delta += 1 - 2 * static_cast<int>((old >> (ent & 31u)) & 1u);
+                    }
+                }
+            };
+            if (p.uni_vdeg && use_regs) {
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        TH vea = ve_handle(warp * D);                                                            \
+        int i = 0;                                                                               \
+        for (int j = warp; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {        \
+            const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
+            if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
+            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
+        }                                                                                        \
+    }
+                BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
+#undef BP_CASE
+                flips = ebits ^ newbits;
+                ebits = newbits;
+            } else {
+                // general degrees and/or more than 64 variables per warp (decision fields in memory)
+                int i = 0;
+                uint32_t neww = 0;
+                for (int j = warp; j < p.n; j += W, ++i) {
+                    const int cp = colptr_at(j);
+                    const int deg = colptr_at(j + 1) - cp;
+                    const TH vea = ve_handle(cp);
+                    double R = p0;                                                    // degree 0: prior only
+#define BP_CASE(D) R = var_node<D>(ml, vea, p0, regular_p0)
+                    BP_DEGREE_SWITCH(
+                        deg, BP_CASE, if (BIG) {
+                            R = var_update_big(
+                                [&](int k) -> double & {
+                                    uint32_t off;
+                                    if constexpr (kStateShared) off = lds_u32(ve_a + 4 * (cp + k));
+                                    else off = __ldg(p.g_ve_off + cp + k);
+                                    return *reinterpret_cast<double *>(msg_generic + off);
+                                },
+                                deg, p0);
+                        })
+#undef BP_CASE
+                    if (p.ratio) p.ratio[sid * p.n + j] = R;
+                    const uint32_t bit = (R >= 1.0) ? 1u : 0u;                        // :164-168 (tie -> 1)
+                    if (use_regs) {
+                        newbits |= static_cast<unsigned long long>(bit) << i;
+                    } else {
+                        neww |= bit << (i & 31);
+                        if ((i & 31) == 31 || j + W >= p.n) {                         // field word complete
+                            uint32_t *fw = efield + static_cast<size_t>(i >> 5) * blockDim.x;
+                            const uint32_t f = *fw ^ neww;
+                            if (f) {
+                                *fw = neww;
+                                apply_flips(f, i & ~31);
+                            }
+                            neww = 0;
+                        }
+                    }
+                }
+                if (use_regs) {
+                    flips = ebits ^ newbits;
+                    ebits = newbits;
+                }
+            }
+            // Only variables whose decision flipped touch the residual syndrome s xor H*e
+            // (syndrome re-check :180-181, kept incrementally; lanes walk their own flips).
+            if (flips) apply_flips(flips, 0);
+            if (delta) atomicAdd(nnz + par * 32 + lane, delta);
+        }
+        __syncthreads();
+        // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)
+        const int cur_nnz = nnz[par * 32 + lane];
+        if (active) { ++iter; fresh = false; }
+        const bool conv = active && cur_nnz == 0;
+        const bool done = active && ((p.early_stop && conv) || iter >= p.max_iters);
+        const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
+        if (done) {
+            // errors[:, sid] = guess (:227): every warp ORs the set bits it owns into the
+            // pre-zeroed packed row
+            auto emit = [&](unsigned long long b, int ibase) {
+                while (b) {
+                    const int j = warp + (ibase + __ffsll(static_cast<long long>(b)) - 1) * W;
+                    b &= b - 1;
+                    atomicOr(p.err_words + sid * p.NW + (j >> 5), 1u << (j & 31));
+                }
+            };
+            if (use_regs) emit(ebits, 0);
+            else
+                for (int k = 0; k < p.nfw; ++k) emit(efield[static_cast<size_t>(k) * blockDim.x], k * 32);
+        }
+        if (warp == 0) {
+            if (done) {
+                p.conv[sid] = conv ? 1 : 0;
+                if (p.iters) p.iters[sid] = iter;
+                n_done += 1; n_conv += conv ? 1 : 0; n_iters += iter;
+            } else {
+                nnz[(par ^ 1) * 32 + lane] = cur_nnz;          // carry over to the other buffer
+            }
+        }
+        par ^= 1;
+        if (done_mask) refill(done_mask, par);
+        __syncthreads();
+    }
+
+    if (warp == 0 && p.counters) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
+            n_conv += __shfl_xor_sync(0xffffffffu, n_conv, o);
+            n_iters += __shfl_xor_sync(0xffffffffu, n_iters, o);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 0, n_done);
+            atomicAdd(p.counters + 1, n_conv);
+            atomicAdd(p.counters + 2, n_iters);
+        }
+    }
+}
+
+}  // namespace bp

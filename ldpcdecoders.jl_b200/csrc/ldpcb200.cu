@@ -17,9 +17,8 @@
 #include <vector>
 
 #include "../../include/ldpcb200.h"
-#include "bp_global.cuh"
+#include "bp_kernel.cuh"
 #include "bp_math.cuh"
-#include "bp_smem.cuh"
 #include "formats.cuh"
 
 namespace {
@@ -76,11 +75,9 @@ struct DeviceCtx {
     // graph tables
     int *d_rowptr = nullptr, *d_colptr = nullptr, *d_ve_slot = nullptr, *d_ve_chk = nullptr;
     unsigned char *d_tables = nullptr;
-    // family GLOBAL state
-    DevBuf msg, syn, resid, errb, sid, iter, flags, nnz;
-    unsigned long long *d_queue = nullptr;
-    unsigned long long *h_queue = nullptr;    // pinned
-    int nslab_alloc = 0;
+    uint32_t *d_ve_off = nullptr, *d_vflip = nullptr;   // wide tables (mode 2)
+    // family GLOBAL stores: per resident CTA messages (+ syndrome state / decision fields when those are global)
+    DevBuf msg, state, efield;
     // host-batch staging
     DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio, counters, scratch;
 };
@@ -104,9 +101,10 @@ struct ldpcb200 {
     int64_t opt_chunk = 0;
     // resolved configuration
     bool configured = false;
-    int family = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0;
-    bool two_ctas = false;
-    bp::SmemParams sp_proto{};
+    int family = 0, mode = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0, shape = 0;
+    int nfw = 0;                 // decision-field words per thread (0: fields live in registers)
+    bool efield_global = false;
+    bp::KernelParams kp_proto{};
     std::vector<DeviceCtx> dev;
     std::atomic<long long> launches{0};
 };
@@ -115,19 +113,29 @@ namespace {
 
 inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-// shared-memory carve-up of family SMEM; returns total bytes
-int smem_layout(const ldpcb200 *h, bp::SmemParams &p)
+// shared-memory carve-up for a kernel mode / thread count; returns total bytes
+//   mode 0: messages | syn | resid | stage | nnz | [efield] | tables | mbar
+//   mode 1:            syn | resid | stage | nnz | [efield] | tables | mbar
+//   mode 2:                                  nnz                      | mbar
+int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_in_smem, bp::KernelParams &p)
 {
-    int off = static_cast<int>(h->E) * 32 * 8;
-    p.off_syn = off;    off += h->SW * 128;
-    p.off_resid = off;  off += h->SW * 128;
-    p.off_stage = off;  off += h->SW * 128;
-    p.off_nnz = off;    off += 2 * 32 * 4;
-    off = align_up(off, 16);
-    p.off_tables = off; off += static_cast<int>(h->tables.size());
-    off = align_up(off, 8);
-    p.off_mbar = off;   off += 8;
-    return align_up(off, 16);
+    long long off = 0;
+    if (mode == 0) off = static_cast<long long>(h->E) * 32 * 8;
+    if (mode <= 1) {
+        p.off_syn = static_cast<int>(off);    off += h->SW * 128;
+        p.off_resid = static_cast<int>(off);  off += h->SW * 128;
+        p.off_stage = static_cast<int>(off);  off += h->SW * 128;
+    }
+    p.off_nnz = static_cast<int>(off);    off += 2 * 32 * 4;
+    p.off_efield = static_cast<int>(off);
+    if (efield_in_smem) off += static_cast<long long>(nfw) * threads * 4;
+    off = (off + 15) / 16 * 16;
+    p.off_tables = static_cast<int>(off);
+    if (mode <= 1) off += static_cast<long long>(h->tables.size());
+    off = (off + 7) / 8 * 8;
+    p.off_mbar = static_cast<int>(off);   off += 8;
+    off = (off + 15) / 16 * 16;
+    return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
 }
 
 int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int base)
@@ -230,8 +238,17 @@ int init_device(ldpcb200 *h, DeviceCtx &d)
         CU(cudaMalloc(&d.d_tables, h->tables.size()));
         CU(cudaMemcpy(d.d_tables, h->tables.data(), h->tables.size(), cudaMemcpyHostToDevice));
     }
-    CU(cudaMalloc(&d.d_queue, 2 * sizeof(unsigned long long)));
-    CU(cudaMallocHost(&d.h_queue, 2 * sizeof(unsigned long long)));
+    {   // wide tables: slot byte offsets and residual (word, bit) of every CSC edge
+        std::vector<uint32_t> off(h->ve_slot.size()), fl(h->ve_slot.size());
+        for (size_t e = 0; e < off.size(); ++e) {
+            off[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
+            fl[e] = static_cast<uint32_t>((h->ve_chk[e] >> 5) * 128 + (h->ve_chk[e] & 31));
+        }
+        CU(cudaMalloc(&d.d_ve_off, sizeof(uint32_t) * off.size()));
+        CU(cudaMemcpy(d.d_ve_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&d.d_vflip, sizeof(uint32_t) * fl.size()));
+        CU(cudaMemcpy(d.d_vflip, fl.data(), sizeof(uint32_t) * fl.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -240,42 +257,87 @@ void destroy_device(DeviceCtx &d)
     cudaSetDevice(d.device);
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_rowptr); cudaFree(d.d_colptr); cudaFree(d.d_ve_slot); cudaFree(d.d_ve_chk);
-    cudaFree(d.d_tables); cudaFree(d.d_queue);
-    if (d.h_queue) cudaFreeHost(d.h_queue);
-    for (DevBuf *b : {&d.msg, &d.syn, &d.resid, &d.errb, &d.sid, &d.iter, &d.flags, &d.nnz, &d.raw_in, &d.raw_out,
+    cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.raw_in, &d.raw_out,
                       &d.syn_words, &d.err_words, &d.conv, &d.iters, &d.ratio, &d.counters, &d.scratch})
         b->release();
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
-template <bool BIG, int MAXT, int MINB>
-int smem_kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
-{
-    auto k = bp::bp_smem_kernel<BIG, MAXT, MINB>;
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes));
-    return 0;
-}
+// Instantiations of the persistent kernel.  Shapes: (threads <= 256, 2 CTAs/SM, <= 128 regs),
+// (<= 320, 2, <= 96 regs), (<= 384, 2, <= 80 regs), (<= 512, 1 CTA/SM, <= 128 regs).
+enum KernelShape { kShape256x2 = 0, kShape320x2 = 1, kShape384x2 = 2, kShape512x1 = 3 };
 
-// Instantiations of the persistent kernel: (threads <= 256, 2 CTAs/SM, <=128 regs),
-// (<= 320, 2 CTAs/SM, <= 96 regs), (<= 384, 2 CTAs/SM, <= 80 regs), (<= 512, 1 CTA/SM).
-enum SmemShape { kShape256x2 = 0, kShape320x2 = 1, kShape384x2 = 2, kShape512x1 = 3 };
-
-int smem_shape(bool two_ctas, int threads)
+int kernel_shape(bool two_ctas, int threads)
 {
     if (!two_ctas) return kShape512x1;
     return threads <= 256 ? kShape256x2 : (threads <= 320 ? kShape320x2 : kShape384x2);
 }
 
-// Warps per CTA: warp w owns checks w, w+W, ... and variables w, w+W, ...; pick the W
-// whose two round-robin splits waste the fewest warp-slots (ties -> more warps, better latency hiding).
-int pick_warps(int64_t s, int64_t n, int wmax)
+template <int MODE, bool BIG, int MAXT, int MINB>
+int kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
+{
+    auto k = bp::bp_persistent_kernel<MODE, BIG, MAXT, MINB>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (MODE == 0) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes));
+    return 0;
+}
+
+template <int MODE, bool BIG>
+int kernel_attrs_for(int shape, int smem_bytes, int threads, int *bps)
+{
+    switch (shape) {
+        case kShape256x2: return kernel_attrs<MODE, BIG, 256, 2>(smem_bytes, threads, bps);
+        case kShape320x2: return kernel_attrs<MODE, BIG, 320, 2>(smem_bytes, threads, bps);
+        case kShape384x2: return kernel_attrs<MODE, BIG, 384, 2>(smem_bytes, threads, bps);
+        default: return kernel_attrs<MODE, BIG, 512, 1>(smem_bytes, threads, bps);
+    }
+}
+
+template <int MODE, bool BIG>
+void kernel_launch_for(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const bp::KernelParams &p)
+{
+    switch (shape) {
+        case kShape256x2: bp::bp_persistent_kernel<MODE, BIG, 256, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        case kShape320x2: bp::bp_persistent_kernel<MODE, BIG, 320, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        case kShape384x2: bp::bp_persistent_kernel<MODE, BIG, 384, 2><<<grid, threads, smem_bytes, st>>>(p); break;
+        default: bp::bp_persistent_kernel<MODE, BIG, 512, 1><<<grid, threads, smem_bytes, st>>>(p); break;
+    }
+}
+
+int kernel_attrs_dispatch(int mode, bool big, int shape, int smem_bytes, int threads, int *bps)
+{
+    switch (mode * 2 + (big ? 1 : 0)) {
+        case 0: return kernel_attrs_for<0, false>(shape, smem_bytes, threads, bps);
+        case 1: return kernel_attrs_for<0, true>(shape, smem_bytes, threads, bps);
+        case 2: return kernel_attrs_for<1, false>(shape, smem_bytes, threads, bps);
+        case 3: return kernel_attrs_for<1, true>(shape, smem_bytes, threads, bps);
+        case 4: return kernel_attrs_for<2, false>(shape, smem_bytes, threads, bps);
+        default: return kernel_attrs_for<2, true>(shape, smem_bytes, threads, bps);
+    }
+}
+
+void kernel_launch_dispatch(int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
+                            const bp::KernelParams &p)
+{
+    switch (mode * 2 + (big ? 1 : 0)) {
+        case 0: kernel_launch_for<0, false>(shape, grid, threads, smem_bytes, st, p); break;
+        case 1: kernel_launch_for<0, true>(shape, grid, threads, smem_bytes, st, p); break;
+        case 2: kernel_launch_for<1, false>(shape, grid, threads, smem_bytes, st, p); break;
+        case 3: kernel_launch_for<1, true>(shape, grid, threads, smem_bytes, st, p); break;
+        case 4: kernel_launch_for<2, false>(shape, grid, threads, smem_bytes, st, p); break;
+        default: kernel_launch_for<2, true>(shape, grid, threads, smem_bytes, st, p); break;
+    }
+}
+
+// Warps per CTA: warp w owns checks w, w+W, ... and variables w, w+W, ...; pick the W whose two
+// round-robin splits waste the fewest warp-slots (ties -> more warps, better latency hiding).
+int pick_warps(int64_t s, int64_t n, int wmin, int wmax)
 {
     double best = -1.0;
     int best_w = wmax;
-    for (int w = 4; w <= wmax; ++w) {
-        if ((n + w - 1) / w > 64) continue;      // decision bit field of a warp is one 64-bit register
+    for (int w = wmin; w <= wmax; ++w) {
         const double ec = s > 0 ? static_cast<double>(s) / (w * ((s + w - 1) / w)) : 1.0;
         const double ev = n > 0 ? static_cast<double>(n) / (w * ((n + w - 1) / w)) : 1.0;
         const double score = 0.6 * ec + 0.4 * ev + 0.004 * w;
@@ -284,94 +346,73 @@ int pick_warps(int64_t s, int64_t n, int wmax)
     return best_w;
 }
 
-template <bool BIG>
-int smem_attrs_for(int shape, int smem_bytes, int threads, int *bps)
-{
-    switch (shape) {
-        case kShape256x2: return smem_kernel_attrs<BIG, 256, 2>(smem_bytes, threads, bps);
-        case kShape320x2: return smem_kernel_attrs<BIG, 320, 2>(smem_bytes, threads, bps);
-        case kShape384x2: return smem_kernel_attrs<BIG, 384, 2>(smem_bytes, threads, bps);
-        default: return smem_kernel_attrs<BIG, 512, 1>(smem_bytes, threads, bps);
-    }
-}
-
-template <bool BIG>
-void smem_launch_for(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const bp::SmemParams &p)
-{
-    switch (shape) {
-        case kShape256x2: bp::bp_smem_kernel<BIG, 256, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        case kShape320x2: bp::bp_smem_kernel<BIG, 320, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        case kShape384x2: bp::bp_smem_kernel<BIG, 384, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        default: bp::bp_smem_kernel<BIG, 512, 1><<<grid, threads, smem_bytes, st>>>(p); break;
-    }
-}
-
-// Resolve family / launch shape from the code size, the options and device 0's limits.
+// Resolve family / kernel mode / launch shape from the code size, the options and device 0's limits.
 int configure(ldpcb200 *h)
 {
     if (h->configured) return 0;
     DeviceCtx &d0 = h->dev[0];
     CU(cudaSetDevice(d0.device));
-    bp::SmemParams sp{};
-    const int need = h->tables.empty() ? 0x7fffffff : smem_layout(h, sp);
-    int family = h->opt_family;
-    const bool smem_ok = need <= d0.smem_optin && h->E > 0;
-    if (family == LDPCB200_FAMILY_AUTO) family = smem_ok ? LDPCB200_FAMILY_SMEM : LDPCB200_FAMILY_GLOBAL;
-    if (family == LDPCB200_FAMILY_SMEM && !smem_ok)
-        return fail(LDPCB200_EUNSUPPORTED, "family SMEM needs %d bytes of shared memory per CTA (limit %d)", need,
-                    d0.smem_optin);
-    h->family = family;
-    if (family == LDPCB200_FAMILY_SMEM) {
-        const bool two = 2 * (need + 1024) <= d0.smem_per_sm;
-        int warps = h->opt_warps > 0 ? h->opt_warps : pick_warps(h->s, h->n, two ? 12 : 16);
-        warps = std::max(1, std::min(two ? 12 : 16, warps));
-        if ((h->n + warps - 1) / warps > 64)
-            return fail(LDPCB200_EUNSUPPORTED, "family SMEM needs ceil(n / warps) <= 64 (n = %lld, warps = %d)", (long long)h->n, warps);
-        h->two_ctas = two;
-        const int shape = smem_shape(two, warps * 32);
-        int bps = 0, rc;
-        for (DeviceCtx &d : h->dev) {
-            CU(cudaSetDevice(d.device));
-            rc = h->big ? smem_attrs_for<true>(shape, need, warps * 32, &bps) : smem_attrs_for<false>(shape, need, warps * 32, &bps);
-            if (rc) return rc;
-        }
-        if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "family SMEM kernel does not fit on an SM");
-        h->warps = warps;
-        h->ctas_per_sm = bps;
-        h->smem_bytes = need;
-        h->sp_proto = sp;
-    } else {
-        // resident slots: enough warp-tasks to fill the GPU, messages preferably L2-sized
-        const double bytes_per_slot = static_cast<double>(std::max<int64_t>(h->E, 1)) * 8.0;
-        int64_t slots = h->opt_slots;
-        if (slots <= 0) {
-            const int64_t for_l2 = static_cast<int64_t>(48.0 * 1048576.0 / bytes_per_slot);
-            const int64_t min_par = (static_cast<int64_t>(d0.sm_count) * 48 + std::max<int64_t>(h->s, 1) - 1) /
-                                    std::max<int64_t>(h->s, 1) * 32;
-            slots = std::max(for_l2, min_par);
-            slots = std::min<int64_t>(slots, 16384);
-        }
-        slots = std::max<int64_t>(32, (slots + 31) / 32 * 32);
-        h->slots = static_cast<int>(slots);
-    }
-    h->configured = true;
-    return 0;
-}
+    const bool narrow = !h->tables.empty();
+    const int per_cta_2 = d0.smem_per_sm / 2 - 1024;          // budget per CTA with two resident CTAs
+    auto fields = [&](int warps) { return h->n <= 64ll * warps ? 0 : static_cast<int>(((h->n + warps - 1) / warps + 31) / 32); };
 
-int ensure_global_state(ldpcb200 *h, DeviceCtx &d, int nslab)
-{
-    if (nslab <= d.nslab_alloc) return 0;
-    int rc;
-    const size_t ns = static_cast<size_t>(nslab) * 32;
-    if ((rc = d.msg.reserve(static_cast<size_t>(nslab) * std::max<int64_t>(h->E, 1) * 32 * 8))) return rc;
-    if ((rc = d.syn.reserve(static_cast<size_t>(nslab) * h->SW * 128))) return rc;
-    if ((rc = d.resid.reserve(static_cast<size_t>(nslab) * h->SW * 128))) return rc;
-    if ((rc = d.errb.reserve(static_cast<size_t>(nslab) * h->NW * 128))) return rc;
-    if ((rc = d.sid.reserve(ns * 8))) return rc;
-    if ((rc = d.iter.reserve(ns * 4))) return rc;
-    if ((rc = d.flags.reserve(ns * 4))) return rc;
-    if ((rc = d.nnz.reserve(ns * 4))) return rc;
-    d.nslab_alloc = nslab;
+    int family = h->opt_family;
+    int mode = -1, warps = 0, shape = 0, need = 0, nfw = 0;
+    bool two = false, ef_global = false;
+    bp::KernelParams kp{};
+
+    // ---- family SMEM (mode 0): messages of 32 syndromes + state + tables in shared memory
+    if (family != LDPCB200_FAMILY_GLOBAL && narrow && h->E > 0) {
+        const int wmax_two = 12, wmax_one = 16;
+        int w = h->opt_warps > 0 ? h->opt_warps : 0;
+        // try two CTAs per SM first
+        int w2 = w ? std::min(w, wmax_two) : pick_warps(h->s, h->n, 4, wmax_two);
+        int f2 = fields(w2);
+        int need2 = smem_layout(h, 0, w2 * 32, f2, true, kp);
+        if (need2 <= per_cta_2) {
+            mode = 0; warps = w2; two = true; need = need2; nfw = f2;
+        } else {
+            int w1 = w ? std::min(w, wmax_one) : pick_warps(h->s, h->n, 8, wmax_one);
+            int f1 = fields(w1);
+            int need1 = smem_layout(h, 0, w1 * 32, f1, true, kp);
+            if (need1 <= d0.smem_optin) { mode = 0; warps = w1; two = false; need = need1; nfw = f1; }
+        }
+        if (mode == 0) family = LDPCB200_FAMILY_SMEM;
+    }
+    if (family == LDPCB200_FAMILY_SMEM && mode != 0)
+        return fail(LDPCB200_EUNSUPPORTED, "family SMEM: messages of 32 syndromes (%lld B) + tables do not fit in shared memory",
+                    static_cast<long long>(h->E) * 256);
+    // ---- family GLOBAL: messages in HBM/L2; state + tables in shared memory (mode 1) if they fit, else global (mode 2)
+    if (mode < 0) {
+        family = LDPCB200_FAMILY_GLOBAL;
+        const int wmax = 12;
+        warps = h->opt_warps > 0 ? std::min(h->opt_warps, 16) : pick_warps(h->s, h->n, 8, wmax);
+        two = warps <= 12;
+        nfw = fields(warps);
+        if (narrow) {
+            const long long ef_bytes = static_cast<long long>(nfw) * warps * 32 * 4;
+            const bool ef_smem = ef_bytes <= 48 * 1024;
+            need = smem_layout(h, 1, warps * 32, nfw, ef_smem, kp);
+            if (need <= (two ? per_cta_2 : d0.smem_optin)) { mode = 1; ef_global = nfw > 0 && !ef_smem; }
+        }
+        if (mode < 0) {
+            mode = 2;
+            need = smem_layout(h, 2, warps * 32, nfw, false, kp);
+            ef_global = nfw > 0;
+        }
+    }
+    shape = kernel_shape(two, warps * 32);
+    int bps = 0, rc;
+    for (DeviceCtx &d : h->dev) {
+        CU(cudaSetDevice(d.device));
+        rc = kernel_attrs_dispatch(mode, h->big, shape, need, warps * 32, &bps);
+        if (rc) return rc;
+    }
+    if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "BP kernel (mode %d, %d threads, %d B smem) does not fit on an SM", mode, warps * 32, need);
+    h->family = family; h->mode = mode; h->warps = warps; h->shape = shape; h->ctas_per_sm = bps;
+    h->smem_bytes = need; h->nfw = nfw; h->efield_global = ef_global; h->kp_proto = kp;
+    h->slots = 32 * bps * d0.sm_count;
+    h->configured = true;
     return 0;
 }
 
@@ -380,8 +421,7 @@ __global__ void add_counters_kernel(unsigned long long *c, unsigned long long de
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(c, decoded);
 }
 
-// Decode B syndromes resident on device `d` (native packed rows).  Stream-ordered for family
-// SMEM; family GLOBAL synchronises the stream internally while it polls for completion.
+// Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
                      uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st)
 {
@@ -399,70 +439,37 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         }
         return 0;
     }
-    if (h->family == LDPCB200_FAMILY_SMEM) {
-        bp::SmemParams p = h->sp_proto;
-        p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
-        p.SW = h->SW; p.NW = h->NW; p.uni_cdeg = h->uni_cdeg; p.uni_vdeg = h->uni_vdeg;
-        p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop; p.p0 = h->p0; p.B = B;
-        p.regular_p0 = h->regular_p0;
-        p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
-        p.counters = counters;
-        p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
-        p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
-        // finished lanes OR their set decision bits into the row: rows start out zero
-        CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
-        const long long nchunks = (B + 31) / 32;
-        const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
-        const int thr = h->warps * 32;
-        if (h->big) smem_launch_for<true>(smem_shape(h->two_ctas, thr), grid, thr, h->smem_bytes, st, p);
-        else smem_launch_for<false>(smem_shape(h->two_ctas, thr), grid, thr, h->smem_bytes, st, p);
-        h->launches++;
-        CU(cudaGetLastError());
-        return 0;
-    }
-    // ---- family GLOBAL
-    const int nslab = static_cast<int>(std::min<int64_t>(h->slots / 32, (B + 31) / 32));
-    int rc = ensure_global_state(h, d, nslab);
-    if (rc) return rc;
-    bp::GlobalParams p{};
+    const long long nchunks = (B + 31) / 32;
+    const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
+    const int thr = h->warps * 32;
+    bp::KernelParams p = h->kp_proto;
     p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
-    p.SW = h->SW; p.NW = h->NW; p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop;
-    p.nslab = nslab; p.p0 = h->p0; p.B = B; p.regular_p0 = h->regular_p0;
+    p.SW = h->SW; p.NW = h->NW; p.uni_cdeg = h->uni_cdeg; p.uni_vdeg = h->uni_vdeg;
+    p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop; p.p0 = h->p0; p.B = B;
+    p.regular_p0 = h->regular_p0;
     p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
     p.counters = counters;
-    p.rowptr = d.d_rowptr; p.colptr = d.d_colptr; p.ve_slot = d.d_ve_slot; p.ve_chk = d.d_ve_chk;
-    p.msg = d.msg.as<double>(); p.syn = d.syn.as<uint32_t>(); p.resid = d.resid.as<uint32_t>();
-    p.errb = d.errb.as<uint32_t>(); p.sid = d.sid.as<long long>(); p.iter = d.iter.as<int>();
-    p.flags = d.flags.as<int>(); p.nnz = d.nnz.as<int>(); p.queue = d.d_queue;
-    CU(cudaMemsetAsync(d.d_queue, 0, 2 * sizeof(unsigned long long), st));
-    bp::bp_global_finish<<<nslab, 256, 0, st>>>(p, 1);
-    h->launches++;
-    const long long cwarps = static_cast<long long>(nslab) * h->s, vwarps = static_cast<long long>(nslab) * h->n;
-    const int cap = d.sm_count * 32;
-    const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((cwarps + 7) / 8, cap)));
-    const int vgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((vwarps + 7) / 8, cap)));
-    const long long NS = static_cast<long long>(nslab) * 32;
-    long long finished = 0;
-    while (finished < B) {
-        // at most NS syndromes can finish per iteration: no need to poll before that many ran
-        long long burst = (B - finished + NS - 1) / NS;
-        burst = std::max<long long>(1, std::min<long long>(burst, 64));
-        if (B - finished <= NS) burst = std::min<long long>(burst + 1, std::max(1, h->max_iters / 8 + 1));
-        for (long long it = 0; it < burst; ++it) {
-            if (h->big) {
-                bp::bp_global_check<true><<<cgrid, 256, 0, st>>>(p);
-                bp::bp_global_var<true><<<vgrid, 256, 0, st>>>(p);
-            } else {
-                bp::bp_global_check<false><<<cgrid, 256, 0, st>>>(p);
-                bp::bp_global_var<false><<<vgrid, 256, 0, st>>>(p);
-            }
-            bp::bp_global_finish<<<nslab, 256, 0, st>>>(p, 0);
-            h->launches += 3;
-        }
-        CU(cudaMemcpyAsync(d.h_queue, d.d_queue, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        finished = static_cast<long long>(d.h_queue[1]);
+    p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
+    p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
+    p.g_rowptr = d.d_rowptr; p.g_colptr = d.d_colptr; p.g_ve_off = d.d_ve_off; p.g_vflip = d.d_vflip;
+    p.nfw = h->nfw;
+    int rc;
+    if (h->mode >= 1) {
+        if ((rc = d.msg.reserve(static_cast<size_t>(grid) * std::max<int64_t>(h->E, 1) * 32 * 8))) return rc;
+        p.msg_global = d.msg.as<double>();
     }
+    if (h->mode == 2) {
+        if ((rc = d.state.reserve(static_cast<size_t>(grid) * 2 * h->SW * 128))) return rc;
+        p.state_global = d.state.as<uint32_t>();
+    }
+    if (h->efield_global) {
+        if ((rc = d.efield.reserve(static_cast<size_t>(grid) * h->nfw * thr * 4))) return rc;
+        p.efield_global = d.efield.as<uint32_t>();
+    }
+    // finished lanes OR their set decision bits into the row: rows start out zero
+    CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
+    kernel_launch_dispatch(h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
+    h->launches++;
     CU(cudaGetLastError());
     return 0;
 }
@@ -669,7 +676,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "chunk") { h->opt_chunk = value; return 0; }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
-    else if (k == "slots") h->opt_slots = static_cast<int>(value);
+    else if (k == "slots") h->opt_slots = static_cast<int>(value);   // accepted for compatibility, unused
     else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
     h->configured = false;
     return 0;
@@ -686,12 +693,13 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
     out->max_check_degree = h->max_cdeg; out->max_var_degree = h->max_vdeg;
     out->family = h->family; out->ndev = static_cast<int>(h->dev.size());
     out->sm_count = h->dev[0].sm_count;
-    out->ctas_per_sm = h->ctas_per_sm; out->threads_per_cta = h->family == LDPCB200_FAMILY_SMEM ? h->warps * 32 : 256;
+    out->ctas_per_sm = h->ctas_per_sm; out->threads_per_cta = h->warps * 32;
     out->smem_bytes = h->smem_bytes; out->slots = h->slots;
     out->syn_words = h->SW; out->err_words = h->NW;
     out->message_bytes = h->family == LDPCB200_FAMILY_SMEM
                              ? 0
                              : static_cast<int64_t>(h->slots) * std::max<int64_t>(h->E, 1) * 8;
+    out->kernel_mode = h->mode;
     return 0;
 }
 
