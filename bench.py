@@ -145,6 +145,7 @@ def run_reference(args):
     # size one step to ~2 s of wall time
     probe = 4096
     _, syn = oracle.sample(H, per, SEED_E, 0, probe)
+    oracle.batch_decode(H, per, mi, syn, nthreads=nthreads)          # spins the thread pool up
     t0 = time.perf_counter()
     oracle.batch_decode(H, per, mi, syn, nthreads=nthreads)
     dt = max(time.perf_counter() - t0, 1e-4)
@@ -168,7 +169,7 @@ def run_reference(args):
             "config": config_dict(args, H, per, mi, B),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, H, per, mi, B):
@@ -182,7 +183,27 @@ def config_dict(args, H, per, mi, B):
             else "L2 flushed between steps (256 MB write)"}
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything libraries print (NCCL banners, warnings) goes to stderr; stdout carries exactly
+    the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -413,7 +434,7 @@ def main():
             line["cpu_baseline_dense_faithful"] = cpu_baseline_leg(oracle, H, per, mi, SEED_E, 5.0, 1, dense=True)
     dec.close()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

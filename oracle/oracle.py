@@ -113,4 +113,9 @@ def threshold(per):
 
 
 def num_threads():
-    return int(load().bp_oracle_num_threads())
+    """Host threads available to this process (affinity-aware); NOT omp_get_max_threads(), which
+    torchrun pins to 1 through OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
