@@ -78,8 +78,14 @@ struct DeviceCtx {
     uint32_t *d_ve_off = nullptr, *d_vflip = nullptr;   // wide tables (mode 2)
     // family GLOBAL stores: per resident CTA messages (+ syndrome state / decision fields when those are global)
     DevBuf msg, state, efield;
-    // host-batch staging
-    DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio, counters, scratch;
+    // host-batch staging: two buffer sets / streams so that the copies of one chunk overlap the
+    // decode of the other
+    struct StageSet {
+        cudaStream_t stream = nullptr;
+        DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio;
+    } set[2];
+    cudaEvent_t decode_done = nullptr;
+    DevBuf counters, scratch;
 };
 
 }  // namespace
@@ -224,6 +230,9 @@ int init_device(ldpcb200 *h, DeviceCtx &d)
     d.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
     d.smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    d.set[0].stream = d.stream;
+    CU(cudaStreamCreateWithFlags(&d.set[1].stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&d.decode_done, cudaEventDisableTiming));
     auto up = [&](int **dst, const std::vector<int> &v) -> int {
         CU(cudaMalloc(dst, sizeof(int) * v.size()));
         CU(cudaMemcpy(*dst, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
@@ -258,9 +267,12 @@ void destroy_device(DeviceCtx &d)
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_rowptr); cudaFree(d.d_colptr); cudaFree(d.d_ve_slot); cudaFree(d.d_ve_chk);
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.raw_in, &d.raw_out,
-                      &d.syn_words, &d.err_words, &d.conv, &d.iters, &d.ratio, &d.counters, &d.scratch})
-        b->release();
+    if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch}) b->release();
+    for (auto &S : d.set)
+        for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio}) b->release();
+    if (d.decode_done) cudaEventDestroy(d.decode_done);
+    if (d.set[1].stream) cudaStreamDestroy(d.set[1].stream);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -496,99 +508,112 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     (void)Btot;
     CU(cudaSetDevice(d.device));
     const int64_t s = h->s, n = h->n;
-    cudaStream_t st = d.stream;
-    // chunk size: bound the staging footprint
+    // chunk size: bound the staging footprint (two sets are in flight)
     const double per_syn = static_cast<double>(fmt_bytes(syn_fmt, s, syn_ld, 2, h->SW) - fmt_bytes(syn_fmt, s, syn_ld, 1, h->SW)) +
                            static_cast<double>(fmt_bytes(err_fmt, n, err_ld, 2, h->NW) - fmt_bytes(err_fmt, n, err_ld, 1, h->NW)) +
                            (h->SW + h->NW) * 4.0 + 5.0 + (ratio ? 8.0 * n : 0.0);
-    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : static_cast<int64_t>(512.0 * 1048576.0 / std::max(per_syn, 1.0));
-    CH = std::max<int64_t>(32, std::min<int64_t>(CH, 1 << 22) / 32 * 32);
+    // about four chunks per call (every chunk ends with a tail of slow syndromes, so fewer is better, but
+    // at least two are needed to overlap copies with decoding), bounded by 256 MB of staging per set
+    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>((Bd + 3) / 4, 32768);
+    CH = std::min<int64_t>(CH, static_cast<int64_t>(256.0 * 1048576.0 / std::max(per_syn, 1.0)));
+    CH = std::max<int64_t>(32, (CH + 31) / 32 * 32);
     int rc;
     if ((rc = d.counters.reserve(LDPCB200_NUM_COUNTERS * 8))) return rc;
-    CU(cudaMemsetAsync(d.counters.p, 0, LDPCB200_NUM_COUNTERS * 8, st));
-    for (int64_t c0 = 0; c0 < Bd; c0 += CH) {
+    CU(cudaMemsetAsync(d.counters.p, 0, LDPCB200_NUM_COUNTERS * 8, d.set[0].stream));
+    CU(cudaStreamSynchronize(d.set[0].stream));
+    bool have_prev_decode = false;
+    int64_t chunk_no = 0;
+    for (int64_t c0 = 0; c0 < Bd; c0 += CH, ++chunk_no) {
+        DeviceCtx::StageSet &S = d.set[chunk_no & 1];
+        cudaStream_t st = S.stream;
+        CU(cudaStreamSynchronize(st));                    // the chunk that used this set two steps ago has landed
         const int64_t Bc = std::min(CH, Bd - c0);
         const int64_t g0 = b0 + c0;                       // first global column of this chunk
-        if ((rc = d.syn_words.reserve(static_cast<size_t>(Bc) * h->SW * 4))) return rc;
-        if ((rc = d.err_words.reserve(static_cast<size_t>(Bc) * h->NW * 4))) return rc;
-        if ((rc = d.conv.reserve(static_cast<size_t>(Bc)))) return rc;
-        if ((rc = d.iters.reserve(static_cast<size_t>(Bc) * 4))) return rc;
-        if (ratio && (rc = d.ratio.reserve(static_cast<size_t>(Bc) * n * 8))) return rc;
+        if ((rc = S.syn_words.reserve(static_cast<size_t>(Bc) * h->SW * 4))) return rc;
+        if ((rc = S.err_words.reserve(static_cast<size_t>(Bc) * h->NW * 4))) return rc;
+        if ((rc = S.conv.reserve(static_cast<size_t>(Bc)))) return rc;
+        if ((rc = S.iters.reserve(static_cast<size_t>(Bc) * 4))) return rc;
+        if (ratio && (rc = S.ratio.reserve(static_cast<size_t>(Bc) * n * 8))) return rc;
         // ---- syndromes -> device -> packed rows
-        uint32_t *syn_words = d.syn_words.as<uint32_t>();
+        uint32_t *syn_words = S.syn_words.as<uint32_t>();
         if (syn_fmt == LDPCB200_FMT_PACKED32) {
             CU(cudaMemcpyAsync(syn_words, static_cast<const uint32_t *>(syndromes) + g0 * h->SW,
                                static_cast<size_t>(Bc) * h->SW * 4, cudaMemcpyHostToDevice, st));
         } else if (syn_fmt == LDPCB200_FMT_BITS) {
             const size_t w0 = static_cast<size_t>(g0 * s / 32);           // g0 is a multiple of 32
             const size_t nw = static_cast<size_t>((Bc * s + 31) / 32);
-            if ((rc = d.raw_in.reserve(nw * 4))) return rc;
-            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const uint32_t *>(syndromes) + w0, nw * 4, cudaMemcpyHostToDevice, st));
-            bp::pack_bits<<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<uint32_t>(), static_cast<long long>(nw),
+            if ((rc = S.raw_in.reserve(nw * 4))) return rc;
+            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const uint32_t *>(syndromes) + w0, nw * 4, cudaMemcpyHostToDevice, st));
+            bp::pack_bits<<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<uint32_t>(), static_cast<long long>(nw),
                                                                             static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
         } else if (syn_fmt == LDPCB200_FMT_U8) {
             const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
-            if ((rc = d.raw_in.reserve(bytes))) return rc;
-            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const uint8_t *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
-            bp::pack_elems<uint8_t><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<uint8_t>(), syn_ld,
+            if ((rc = S.raw_in.reserve(bytes))) return rc;
+            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const uint8_t *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            bp::pack_elems<uint8_t><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<uint8_t>(), syn_ld,
                                                                                      static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
         } else if (syn_fmt == LDPCB200_FMT_I64) {
             const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
-            if ((rc = d.raw_in.reserve(bytes))) return rc;
-            CU(cudaMemcpyAsync(d.raw_in.p, static_cast<const long long *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
-            bp::pack_elems<long long><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(d.raw_in.as<long long>(), syn_ld,
+            if ((rc = S.raw_in.reserve(bytes))) return rc;
+            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const long long *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            bp::pack_elems<long long><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<long long>(), syn_ld,
                                                                                        static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
         } else {
             return fail(LDPCB200_EINVAL, "unsupported syndrome format %d", syn_fmt);
         }
-        // ---- decode
-        rc = decode_on_device(h, d, Bc, syn_words, d.err_words.as<uint32_t>(), d.conv.as<uint8_t>(), d.iters.as<int32_t>(),
-                              ratio ? d.ratio.as<double>() : nullptr, d.counters.as<unsigned long long>(), st);
+        // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
+        if (have_prev_decode) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
+        rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
+                              ratio ? S.ratio.as<double>() : nullptr, d.counters.as<unsigned long long>(), st);
         if (rc) return rc;
+        CU(cudaEventRecord(d.decode_done, st));
+        have_prev_decode = true;
         // ---- packed rows -> caller's format -> host
-        const uint32_t *ew = d.err_words.as<uint32_t>();
+        const uint32_t *ew = S.err_words.as<uint32_t>();
         if (err_fmt == LDPCB200_FMT_PACKED32) {
             CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + g0 * h->NW, ew, static_cast<size_t>(Bc) * h->NW * 4,
                                cudaMemcpyDeviceToHost, st));
         } else if (err_fmt == LDPCB200_FMT_BITS) {
             const size_t w0 = static_cast<size_t>(g0 * n / 32);
             const size_t nw = static_cast<size_t>((Bc * n + 31) / 32);
-            if ((rc = d.raw_out.reserve(nw * 4))) return rc;
+            if ((rc = S.raw_out.reserve(nw * 4))) return rc;
             bp::unpack_bits<<<grid_for(static_cast<long long>(nw), d.sm_count), 256, 0, st>>>(
-                ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<uint32_t>(), static_cast<long long>(nw));
+                ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<uint32_t>(), static_cast<long long>(nw));
             h->launches++;
-            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + w0, d.raw_out.p, nw * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + w0, S.raw_out.p, nw * 4, cudaMemcpyDeviceToHost, st));
         } else if (err_fmt == LDPCB200_FMT_U8 || err_fmt == LDPCB200_FMT_I64 || err_fmt == LDPCB200_FMT_F64) {
             const size_t bytes = fmt_bytes(err_fmt, n, err_ld, Bc, h->NW);
-            if ((rc = d.raw_out.reserve(bytes))) return rc;
+            if ((rc = S.raw_out.reserve(bytes))) return rc;
             const int g = grid_for(Bc * h->NW, d.sm_count);
-            if (err_ld != n) CU(cudaMemsetAsync(d.raw_out.p, 0, bytes, st));
+            if (err_ld != n) CU(cudaMemsetAsync(S.raw_out.p, 0, bytes, st));
             if (err_fmt == LDPCB200_FMT_U8)
-                bp::unpack_elems<uint8_t><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<uint8_t>(), err_ld);
+                bp::unpack_elems<uint8_t><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<uint8_t>(), err_ld);
             else if (err_fmt == LDPCB200_FMT_I64)
-                bp::unpack_elems<long long><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<long long>(), err_ld);
+                bp::unpack_elems<long long><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<long long>(), err_ld);
             else
-                bp::unpack_elems<double><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, d.raw_out.as<double>(), err_ld);
+                bp::unpack_elems<double><<<g, 256, 0, st>>>(ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<double>(), err_ld);
             h->launches++;
             const size_t esz = err_fmt == LDPCB200_FMT_U8 ? 1 : 8;
             if (err_ld == n) {
-                CU(cudaMemcpyAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, d.raw_out.p, bytes,
+                CU(cudaMemcpyAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, S.raw_out.p, bytes,
                                    cudaMemcpyDeviceToHost, st));
             } else {   // strided destination: only the n rows of each column belong to the caller
                 CU(cudaMemcpy2DAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, err_ld * esz,
-                                     d.raw_out.p, err_ld * esz, n * esz, Bc, cudaMemcpyDeviceToHost, st));
+                                     S.raw_out.p, err_ld * esz, n * esz, Bc, cudaMemcpyDeviceToHost, st));
             }
         } else {
             return fail(LDPCB200_EINVAL, "unsupported error format %d", err_fmt);
         }
-        CU(cudaMemcpyAsync(converged + g0, d.conv.p, static_cast<size_t>(Bc), cudaMemcpyDeviceToHost, st));
-        if (iters) CU(cudaMemcpyAsync(iters + g0, d.iters.p, static_cast<size_t>(Bc) * 4, cudaMemcpyDeviceToHost, st));
-        if (ratio) CU(cudaMemcpyAsync(ratio + g0 * n, d.ratio.p, static_cast<size_t>(Bc) * n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpyAsync(converged + g0, S.conv.p, static_cast<size_t>(Bc), cudaMemcpyDeviceToHost, st));
+        if (iters) CU(cudaMemcpyAsync(iters + g0, S.iters.p, static_cast<size_t>(Bc) * 4, cudaMemcpyDeviceToHost, st));
+        if (ratio) CU(cudaMemcpyAsync(ratio + g0 * n, S.ratio.p, static_cast<size_t>(Bc) * n * 8, cudaMemcpyDeviceToHost, st));
     }
+    CU(cudaStreamSynchronize(d.set[0].stream));
+    CU(cudaStreamSynchronize(d.set[1].stream));
+    cudaStream_t st = d.set[0].stream;
     unsigned long long hc[LDPCB200_NUM_COUNTERS];
     CU(cudaMemcpyAsync(hc, d.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
