@@ -37,7 +37,7 @@ def workload_spec(args, pkg):
     H, per, mi = pkg.codes.config_matrix(args.workload)
     default_per = {"C1": 0.01, "C2": 0.01, "C3": 0.03, "C4": 0.02, "C5": 0.02}[args.workload]
     per = args.per if args.per is not None else default_per
-    default_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 4096}[args.workload]
+    default_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 16384}[args.workload]
     B = args.batch if args.batch is not None else default_B
     if args.max_iters is not None:
         mi = args.max_iters
@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--family", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=-1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -244,6 +245,8 @@ def main():
         opts["family"] = args.family
     if args.warps:
         opts["warps"] = args.warps
+    if args.prefetch >= 0:
+        opts["prefetch"] = args.prefetch
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], **opts)
     info = dec.info()
     SW, NW = info["syn_words"], info["err_words"]
@@ -353,7 +356,8 @@ def main():
             "mean_iters": mean_iters, "converged_frac": conv_frac, "exact_match_frac": exact_frac,
             "syndrome_iterations_per_s": float(c[2]) / secs,
             "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
-            "kernel": {k: info[k] for k in ("family", "ctas_per_sm", "threads_per_cta", "smem_bytes", "slots", "message_bytes")}}
+            "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "smem_bytes", "slots",
+                                            "message_bytes", "prefetch_distance")}}
 
     # ---- end to end through the host-buffer C-ABI call (Julia BitMatrix in / out), pinned memory
     if not args.no_e2e:

@@ -65,7 +65,7 @@ typedef struct {
     int32_t syn_words, err_words; /* uint32 words per packed syndrome / error row */
     int64_t message_bytes;      /* device bytes of the message store per device (family GLOBAL) */
     int32_t kernel_mode;        /* 0: all in shared memory, 1: messages in HBM/L2, 2: messages + state + tables in HBM/L2 */
-    int32_t reserved_;
+    int32_t prefetch_distance;  /* cp.async ring depth of modes 1/2 (0 = messages read directly) */
 } ldpcb200_info_t;
 
 /* counters[] layout of the decode calls (summed over all devices of the handle) */
@@ -92,7 +92,8 @@ int ldpcb200_destroy(ldpcb200_t *h);
 int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
 
 /* Tunables, set before the first decode (all optional):
- *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA),
+ *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA), "prefetch" (cp.async prefetch distance of the
+ *   HBM modes, 0..3),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);

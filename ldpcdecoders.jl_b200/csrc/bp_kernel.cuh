@@ -70,8 +70,11 @@ struct KernelParams {
     // [word][thread]; in shared memory (off_efield) or, if efield_global != null, per CTA in HBM
     int nfw;
     uint32_t *efield_global;
+    // modes 1/2: per-warp shared-memory ring that message rows are prefetched into with cp.async
+    // (pd + 1 slots of ring_slot_bytes each; pd = prefetch distance in nodes, 0 = no staging)
+    int pd, ring_slot_bytes, ring_warp_bytes;
     // shared-memory carve-up (byte offsets from the dynamic smem base)
-    int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield;
+    int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield, off_ring;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -113,6 +116,21 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n (0..3) of the most recent groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(int n)
+{
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
 
 
 // ---- message / table accessors.  Shared-window handles are 32-bit shared-space addresses
@@ -203,6 +221,33 @@ __device__ __forceinline__ double var_node(MH ml, TH vea, double p0, bool regula
     load_offsets<D>(v, vea);
 #pragma unroll
     for (int k = 0; k < D; ++k) m[k] = ld_msg(ml + v[k]);
+    const double R = var_update<D>(m, p0, regular_p0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);
+    return R;
+}
+
+// Staged forms (modes 1/2): the node's rows were prefetched into a shared-memory ring slot
+// (`ra`, this lane's column); results go straight back to global memory.
+template <int D>
+__device__ __forceinline__ void check_node_staged(uint32_t ra, unsigned char *ga, bool neg, bool fresh, double p0)
+{
+    double m[D];
+    load_row<D>(m, ra);
+    if (fresh) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) m[k] = p0;
+    }
+    check_update<D>(m, neg);
+    store_row<D>(m, ga);
+}
+template <int D, class TH>
+__device__ __forceinline__ double var_node_staged(uint32_t ra, unsigned char *ml, TH vea, double p0, bool regular_p0)
+{
+    uint32_t v[D];
+    double m[D];
+    load_offsets<D>(v, vea);
+    load_row<D>(m, ra);
     const double R = var_update<D>(m, p0, regular_p0);
 #pragma unroll
     for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);
@@ -354,7 +399,60 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     while (__ballot_sync(0xffffffffu, active) != 0u) {
         // ------------------------------------------------------------------ check pass (:135-150)
         // warp w owns checks w, w+W, ...; syndrome bit of check i = bit i%32 of syn[i/32][lane]
-        if (active) {
+        bool staged = false;
+        if constexpr (!kMsgShared) staged = p.pd > 0;
+        if (staged) {
+            // Messages live in HBM/L2: the whole warp (active lanes or not) streams the rows of its
+            // next pd checks into a shared-memory ring with 16-byte cp.async.cg copies (two 256 B rows
+            // per instruction), so pd nodes' worth of loads are always in flight per warp.
+            if constexpr (!kMsgShared) {
+                const int nslot = p.pd + 1;
+                const uint32_t ring_w = sbase + p.off_ring + warp * p.ring_warp_bytes;
+                unsigned char *cta_msg = msg_generic - lane * 8;
+                auto span = [&](int i, int &rp, int &deg) {
+                    if (p.uni_cdeg) { deg = p.uni_cdeg; rp = i * deg; }
+                    else { rp = rowptr_at(i); deg = rowptr_at(i + 1) - rp; }
+                };
+                auto issue = [&](int i, int slot) {
+                    if (i < p.s) {
+                        int rp, deg;
+                        span(i, rp, deg);
+                        if (deg <= kMaxRegDegree) {
+                            const uint32_t dst = ring_w + slot * p.ring_slot_bytes + (lane & 15) * 16;
+                            const unsigned char *src = cta_msg + static_cast<size_t>(rp) * 256 + (lane & 15) * 16;
+                            for (int k = lane >> 4; k < deg; k += 2) cp_async16(dst + k * 256, src + static_cast<size_t>(k) * 256);
+                        }
+                    }
+                    cp_async_commit();
+                };
+                int islot = 0;
+                for (int t = 0; t < p.pd; ++t) { issue(warp + t * W, islot); islot = (islot + 1 == nslot) ? 0 : islot + 1; }
+                int cslot = 0;
+                for (int i = warp; i < p.s; i += W) {
+                    issue(i + p.pd * W, islot);
+                    islot = (islot + 1 == nslot) ? 0 : islot + 1;
+                    cp_async_wait_pending(p.pd);
+                    __syncwarp();
+                    if (active) {
+                        int rp, deg;
+                        span(i, rp, deg);
+                        const bool neg = syn_bit(i);
+                        const uint32_t ra = ring_w + cslot * p.ring_slot_bytes + lane * 8;
+                        unsigned char *ga = msg_generic + static_cast<size_t>(rp) * 256;
+#define BP_CASE(D) check_node_staged<D>(ra, ga, neg, fresh, p0)
+                        BP_DEGREE_SWITCH(
+                            deg, BP_CASE, if (BIG) {
+                                double *base = reinterpret_cast<double *>(ga);
+                                check_update_big([&](int k) -> double & { return base[k * 32]; }, deg, neg, fresh, p0);
+                            })
+#undef BP_CASE
+                    }
+                    __syncwarp();                       // slot is free for the copy issued next iteration
+                    cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;
+                }
+                cp_async_wait_all();
+            }
+        } else if (active) {
             if (p.uni_cdeg) {
                 // every check has the same degree: slots of check i start at i*D, no table reads
 #define BP_CASE(D)                                                                               \
@@ -383,9 +481,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
         __syncthreads();
         // --------------------------------------------------------------- variable pass (:152-178)
         // warp w owns variables w, w+W, ...; decision of its i-th variable = bit i of newbits
-        if (active) {
+        {
             unsigned long long newbits = 0;
             unsigned long long flips = 0;
+            uint32_t neww = 0;
             int delta = 0;
             // a lane walks its flipped variables (bits of f, first bit = variable index ibase)
             auto apply_flips = [&](unsigned long long f, int ibase) {
@@ -400,7 +499,81 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                     }
                 }
             };
-            if (p.uni_vdeg && use_regs) {
+            // posterior ratio R of this lane's i-th variable j: optional output, hard decision (:163-168)
+            auto record = [&](int j, int i, double R) {
+                if (p.ratio) p.ratio[sid * p.n + j] = R;
+                const uint32_t bit = (R >= 1.0) ? 1u : 0u;                            // tie -> 1
+                if (use_regs) {
+                    newbits |= static_cast<unsigned long long>(bit) << i;
+                } else {
+                    neww |= bit << (i & 31);
+                    if ((i & 31) == 31 || j + W >= p.n) {                             // field word complete
+                        uint32_t *fw = efield + static_cast<size_t>(i >> 5) * blockDim.x;
+                        const uint32_t f = *fw ^ neww;
+                        if (f) {
+                            *fw = neww;
+                            apply_flips(f, i & ~31);
+                        }
+                        neww = 0;
+                    }
+                }
+            };
+            if (staged) {
+                if constexpr (!kMsgShared) {
+                    const int nslot = p.pd + 1;
+                    const uint32_t ring_w = sbase + p.off_ring + warp * p.ring_warp_bytes;
+                    unsigned char *cta_msg = msg_generic - lane * 8;
+                    auto span = [&](int j, int &cp, int &deg) {
+                        if (p.uni_vdeg) { deg = p.uni_vdeg; cp = j * deg; }
+                        else { cp = colptr_at(j); deg = colptr_at(j + 1) - cp; }
+                    };
+                    auto off_at = [&](int e) -> uint32_t {
+                        if constexpr (kStateShared) return lds_u32(ve_a + 4 * e);
+                        else return __ldg(p.g_ve_off + e);
+                    };
+                    auto issue = [&](int j, int slot) {
+                        if (j < p.n) {
+                            int cp, deg;
+                            span(j, cp, deg);
+                            if (deg <= kMaxRegDegree) {
+                                const uint32_t dst = ring_w + slot * p.ring_slot_bytes + (lane & 15) * 16;
+                                for (int k = lane >> 4; k < deg; k += 2)
+                                    cp_async16(dst + k * 256, cta_msg + off_at(cp + k) + (lane & 15) * 16);
+                            }
+                        }
+                        cp_async_commit();
+                    };
+                    int islot = 0;
+                    for (int t = 0; t < p.pd; ++t) { issue(warp + t * W, islot); islot = (islot + 1 == nslot) ? 0 : islot + 1; }
+                    int cslot = 0, i = 0;
+                    for (int j = warp; j < p.n; j += W, ++i) {
+                        issue(j + p.pd * W, islot);
+                        islot = (islot + 1 == nslot) ? 0 : islot + 1;
+                        cp_async_wait_pending(p.pd);
+                        __syncwarp();
+                        if (active) {
+                            int cp, deg;
+                            span(j, cp, deg);
+                            const uint32_t ra = ring_w + cslot * p.ring_slot_bytes + lane * 8;
+                            const TH vea = ve_handle(cp);
+                            double R = p0;                                            // degree 0: prior only
+#define BP_CASE(D) R = var_node_staged<D>(ra, msg_generic, vea, p0, regular_p0)
+                            BP_DEGREE_SWITCH(
+                                deg, BP_CASE, if (BIG) {
+                                    R = var_update_big(
+                                        [&](int k) -> double & { return *reinterpret_cast<double *>(msg_generic + off_at(cp + k)); },
+                                        deg, p0);
+                                })
+#undef BP_CASE
+                            record(j, i, R);
+                        }
+                        __syncwarp();
+                        cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;
+                    }
+                    cp_async_wait_all();
+                }
+            } else if (active) {
+                if (p.uni_vdeg && use_regs) {
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         TH vea = ve_handle(warp * D);                                                            \
@@ -411,58 +584,43 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
         }                                                                                        \
     }
-                BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
+                    BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
 #undef BP_CASE
-                flips = ebits ^ newbits;
-                ebits = newbits;
-            } else {
-                // general degrees and/or more than 64 variables per warp (decision fields in memory)
-                int i = 0;
-                uint32_t neww = 0;
-                for (int j = warp; j < p.n; j += W, ++i) {
-                    const int cp = colptr_at(j);
-                    const int deg = colptr_at(j + 1) - cp;
-                    const TH vea = ve_handle(cp);
-                    double R = p0;                                                    // degree 0: prior only
+                } else {
+                    // general degrees and/or more than 64 variables per warp (decision fields in memory)
+                    int i = 0;
+                    for (int j = warp; j < p.n; j += W, ++i) {
+                        const int cp = colptr_at(j);
+                        const int deg = colptr_at(j + 1) - cp;
+                        const TH vea = ve_handle(cp);
+                        double R = p0;                                                // degree 0: prior only
 #define BP_CASE(D) R = var_node<D>(ml, vea, p0, regular_p0)
-                    BP_DEGREE_SWITCH(
-                        deg, BP_CASE, if (BIG) {
-                            R = var_update_big(
-                                [&](int k) -> double & {
-                                    uint32_t off;
-                                    if constexpr (kStateShared) off = lds_u32(ve_a + 4 * (cp + k));
-                                    else off = __ldg(p.g_ve_off + cp + k);
-                                    return *reinterpret_cast<double *>(msg_generic + off);
-                                },
-                                deg, p0);
-                        })
+                        BP_DEGREE_SWITCH(
+                            deg, BP_CASE, if (BIG) {
+                                R = var_update_big(
+                                    [&](int k) -> double & {
+                                        uint32_t off;
+                                        if constexpr (kStateShared) off = lds_u32(ve_a + 4 * (cp + k));
+                                        else off = __ldg(p.g_ve_off + cp + k);
+                                        return *reinterpret_cast<double *>(msg_generic + off);
+                                    },
+                                    deg, p0);
+                            })
 #undef BP_CASE
-                    if (p.ratio) p.ratio[sid * p.n + j] = R;
-                    const uint32_t bit = (R >= 1.0) ? 1u : 0u;                        // :164-168 (tie -> 1)
-                    if (use_regs) {
-                        newbits |= static_cast<unsigned long long>(bit) << i;
-                    } else {
-                        neww |= bit << (i & 31);
-                        if ((i & 31) == 31 || j + W >= p.n) {                         // field word complete
-                            uint32_t *fw = efield + static_cast<size_t>(i >> 5) * blockDim.x;
-                            const uint32_t f = *fw ^ neww;
-                            if (f) {
-                                *fw = neww;
-                                apply_flips(f, i & ~31);
-                            }
-                            neww = 0;
-                        }
+                        record(j, i, R);
                     }
                 }
+            }
+            if (active) {
                 if (use_regs) {
                     flips = ebits ^ newbits;
                     ebits = newbits;
                 }
+                // Only variables whose decision flipped touch the residual syndrome s xor H*e
+                // (syndrome re-check :180-181, kept incrementally; lanes walk their own flips).
+                if (flips) apply_flips(flips, 0);
+                if (delta) atomicAdd(nnz + par * 32 + lane, delta);
             }
-            // Only variables whose decision flipped touch the residual syndrome s xor H*e
-            // (syndrome re-check :180-181, kept incrementally; lanes walk their own flips).
-            if (flips) apply_flips(flips, 0);
-            if (delta) atomicAdd(nnz + par * 32 + lane, delta);
         }
         __syncthreads();
         // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)

@@ -105,6 +105,7 @@ struct ldpcb200 {
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
+    int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     // resolved configuration
     bool configured = false;
     int family = 0, mode = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0, shape = 0;
@@ -123,7 +124,7 @@ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 //   mode 0: messages | syn | resid | stage | nnz | [efield] | tables | mbar
 //   mode 1:            syn | resid | stage | nnz | [efield] | tables | mbar
 //   mode 2:                                  nnz                      | mbar
-int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_in_smem, bp::KernelParams &p)
+int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_in_smem, int pd, bp::KernelParams &p)
 {
     long long off = 0;
     if (mode == 0) off = static_cast<long long>(h->E) * 32 * 8;
@@ -140,6 +141,14 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
     if (mode <= 1) off += static_cast<long long>(h->tables.size());
     off = (off + 7) / 8 * 8;
     p.off_mbar = static_cast<int>(off);   off += 8;
+    off = (off + 127) / 128 * 128;
+    // cp.async ring (modes 1/2): per warp pd+1 slots of one node's rows (max register degree)
+    const int maxdeg = std::min(std::max(h->max_cdeg, h->max_vdeg), bp::kMaxRegDegree);
+    p.pd = (mode >= 1) ? pd : 0;
+    p.ring_slot_bytes = std::max(maxdeg, 1) * 256;
+    p.ring_warp_bytes = (p.pd + 1) * p.ring_slot_bytes;
+    p.off_ring = static_cast<int>(off);
+    if (p.pd > 0) off += static_cast<long long>(threads / 32) * p.ring_warp_bytes;
     off = (off + 15) / 16 * 16;
     return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
 }
@@ -380,13 +389,13 @@ int configure(ldpcb200 *h)
         // try two CTAs per SM first
         int w2 = w ? std::min(w, wmax_two) : pick_warps(h->s, h->n, 4, wmax_two);
         int f2 = fields(w2);
-        int need2 = smem_layout(h, 0, w2 * 32, f2, true, kp);
+        int need2 = smem_layout(h, 0, w2 * 32, f2, true, 0, kp);
         if (need2 <= per_cta_2) {
             mode = 0; warps = w2; two = true; need = need2; nfw = f2;
         } else {
             int w1 = w ? std::min(w, wmax_one) : pick_warps(h->s, h->n, 8, wmax_one);
             int f1 = fields(w1);
-            int need1 = smem_layout(h, 0, w1 * 32, f1, true, kp);
+            int need1 = smem_layout(h, 0, w1 * 32, f1, true, 0, kp);
             if (need1 <= d0.smem_optin) { mode = 0; warps = w1; two = false; need = need1; nfw = f1; }
         }
         if (mode == 0) family = LDPCB200_FAMILY_SMEM;
@@ -401,17 +410,24 @@ int configure(ldpcb200 *h)
         warps = h->opt_warps > 0 ? std::min(h->opt_warps, 16) : pick_warps(h->s, h->n, 8, wmax);
         two = warps <= 12;
         nfw = fields(warps);
+        const int pd_max = h->opt_pd >= 0 ? std::min(h->opt_pd, 3) : 3;
+        const int budget = two ? per_cta_2 : d0.smem_optin;
         if (narrow) {
             const long long ef_bytes = static_cast<long long>(nfw) * warps * 32 * 4;
-            const bool ef_smem = ef_bytes <= 48 * 1024;
-            need = smem_layout(h, 1, warps * 32, nfw, ef_smem, kp);
-            if (need <= (two ? per_cta_2 : d0.smem_optin)) { mode = 1; ef_global = nfw > 0 && !ef_smem; }
+            const bool ef_smem = ef_bytes <= 32 * 1024;
+            for (int pd = pd_max; pd >= 0 && mode < 0; --pd) {
+                need = smem_layout(h, 1, warps * 32, nfw, ef_smem, pd, kp);
+                if (need <= budget) { mode = 1; ef_global = nfw > 0 && !ef_smem; }
+            }
         }
         if (mode < 0) {
-            mode = 2;
-            need = smem_layout(h, 2, warps * 32, nfw, false, kp);
+            for (int pd = pd_max; pd >= 0 && mode < 0; --pd) {
+                need = smem_layout(h, 2, warps * 32, nfw, false, pd, kp);
+                if (need <= budget) mode = 2;
+            }
             ef_global = nfw > 0;
         }
+        if (mode < 0) return fail(LDPCB200_EUNSUPPORTED, "no kernel configuration fits in shared memory");
     }
     shape = kernel_shape(two, warps * 32);
     int bps = 0, rc;
@@ -701,6 +717,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "chunk") { h->opt_chunk = value; return 0; }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "slots") h->opt_slots = static_cast<int>(value);   // accepted for compatibility, unused
     else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
     h->configured = false;
@@ -725,6 +742,7 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
                              ? 0
                              : static_cast<int64_t>(h->slots) * std::max<int64_t>(h->E, 1) * 8;
     out->kernel_mode = h->mode;
+    out->prefetch_distance = h->kp_proto.pd;
     return 0;
 }
 
