@@ -38,6 +38,10 @@
 
 #include "bp_math.cuh"
 
+#ifndef BP_PIPELINE_VARS
+#define BP_PIPELINE_VARS 0
+#endif
+
 namespace bp {
 
 struct KernelParams {
@@ -258,6 +262,7 @@ template <int MODE, bool BIG, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_constant__ KernelParams p)
 {
     constexpr bool kMsgShared = MODE == 0;
+    constexpr bool kPipelineVars = BP_PIPELINE_VARS != 0;
     constexpr bool kStateShared = MODE <= 1;
     using MH = typename std::conditional<kMsgShared, uint32_t, unsigned char *>::type;   // message column handle
     using TH = typename std::conditional<kStateShared, uint32_t, const uint32_t *>::type;  // slot-offset table handle
@@ -574,8 +579,31 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 }
             } else if (active) {
                 if (p.uni_vdeg && use_regs) {
+                    // low degrees are software-pipelined: the next variable's slot offsets and
+                    // messages are fetched while the current one is being multiplied out
 #define BP_CASE(D)                                                                               \
-    {                                                                                            \
+    if constexpr (D <= 4 && kPipelineVars) {                                                     \
+        TH vea = ve_handle(warp * D);                                                            \
+        uint32_t v[D], vn[D];                                                                    \
+        double m[D], mn[D];                                                                      \
+        if (warp < p.n) {                                                                        \
+            load_offsets<D>(v, vea);                                                             \
+            _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = ld_msg(ml + v[k]);              \
+        }                                                                                        \
+        int i = 0;                                                                               \
+        for (int j = warp; j < p.n; j += W, ++i) {                                               \
+            vea += W * D * (kStateShared ? 4 : 1);                                               \
+            if (j + W < p.n) {                                                                   \
+                load_offsets<D>(vn, vea);                                                        \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) mn[k] = ld_msg(ml + vn[k]);        \
+            }                                                                                    \
+            const double R = var_update<D>(m, p0, regular_p0);                                   \
+            _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);               \
+            if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
+            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
+            _Pragma("unroll") for (int k = 0; k < D; ++k) { v[k] = vn[k]; m[k] = mn[k]; }        \
+        }                                                                                        \
+    } else {                                                                                     \
         TH vea = ve_handle(warp * D);                                                            \
         int i = 0;                                                                               \
         for (int j = warp; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {        \
