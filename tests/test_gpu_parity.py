@@ -316,3 +316,56 @@ def test_golden_fixtures_on_gpu(pkg, fixture):
     assert np.array_equal(g["converged"], z["converged"])
     assert np.array_equal(g["iters"], z["iters"])
     assert np.array_equal(g["ratio"].view(np.uint64), z["ratio_bits"])
+
+
+def _random_code(rng, s, n, col_deg):
+    rows = np.concatenate([rng.choice(s, size=col_deg, replace=False) for _ in range(n)])
+    cols = np.repeat(np.arange(n), col_deg)
+    return sp.csc_matrix((np.ones(len(rows), dtype=np.uint8), (rows, cols)), shape=(s, n))
+
+
+def test_decision_fields_in_memory(pkg, oracle):
+    """Codes where a warp owns more than 64 variables keep their decisions as bit fields in
+    shared memory (modes 0/1) or in HBM (mode 1 with many variables, mode 2)."""
+    rng = np.random.default_rng(11)
+    cases = [
+        # (H, warps option, expected family)   n / warps > 64 in every case
+        (_random_code(rng, 60, 400, 1), 4, SMEM),        # mode 0, fields in shared memory
+        (_random_code(rng, 300, 2000, 2), 8, GLOBAL),    # mode 1, fields in shared memory
+        (_random_code(rng, 3000, 9000, 2), 12, GLOBAL),  # mode 1, fields in HBM
+    ]
+    for H, warps, fam in cases:
+        s, n = H.shape
+        e = (rng.random((n, 150)) < 0.01).astype(np.uint8)
+        syn = np.asarray((H @ e) % 2).astype(np.uint8)
+        ref = oracle.batch_decode(H, 0.01, 12, syn, want_ratio=True, nthreads=oracle.num_threads())
+        g = run_gpu(pkg, H, 0.01, 12, syn, want_ratio=True, warps=warps)
+        assert g["info"]["family"] == fam and n > 64 * (g["info"]["threads_per_cta"] // 32), g["info"]
+        assert_same(g, ref, want_ratio=True)
+
+
+def test_staging_depths_agree(pkg, oracle, codes):
+    """HBM modes: the cp.async ring (prefetch 1..3) and the direct path give the same bits."""
+    H, _, mi = codes.config_matrix("C4")
+    _, syn = oracle.sample(H, 0.04, 21, 0, 300)
+    ref = oracle.batch_decode(H, 0.04, mi, syn, nthreads=oracle.num_threads())
+    for pf in (0, 1, 2, 3):
+        assert_same(run_gpu(pkg, H, 0.04, mi, syn, prefetch=pf), ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_in_library_sharding_over_two_devices(pkg, oracle, codes):
+    """devices = [0, 1]: the library splits the batch into contiguous column ranges (boundaries
+    multiples of 32) and sums the counters; results equal the single-device ones."""
+    H, _, mi = codes.config_matrix("C3")
+    B = 100_003
+    _, syn = oracle.sample(H, 0.05, 77, 0, B)
+    ref = oracle.batch_decode(H, 0.05, mi, syn, nthreads=oracle.num_threads())
+    dec = pkg.BeliefPropagationDecoder(H, 0.05, mi, devices=[0, 1])
+    assert dec.info()["ndev"] == 2
+    errors = np.zeros((H.shape[1], B), dtype=np.uint8, order="F")
+    iters = np.zeros(B, dtype=np.int32)
+    _, success = pkg.batchdecode_b(dec, syn, errors, iters=iters)
+    g = dict(errors=errors, converged=success, iters=iters, counters=dec.last_counters)
+    dec.close()
+    assert_same(g, ref)
