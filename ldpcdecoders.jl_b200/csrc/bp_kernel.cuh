@@ -258,6 +258,28 @@ __device__ __forceinline__ double var_node_staged(uint32_t ra, unsigned char *ml
     return R;
 }
 
+// Residual-syndrome update for the flipped variables of a lane when every variable has degree D:
+// variable j's D (word, bit) entries sit at vflip[j*D ..], no column-pointer reads.  `resid_lane`
+// points at this lane's column of the residual words ([word][32] layout).  Returns the change of
+// the number of unsatisfied checks.
+template <int D, class VF>
+__device__ __forceinline__ int flip_walk_uniform(uint32_t f, int ibase, int warp, int W, VF vflip_at, uint32_t *resid_lane)
+{
+    int delta = 0;
+    while (f) {
+        const int b = __ffs(static_cast<int>(f)) - 1;
+        f &= f - 1;
+        const int e0 = (warp + (ibase + b) * W) * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const uint32_t ent = vflip_at(e0 + k);                        // (check/32)*128 + check%32
+            const uint32_t old = atomicXor(resid_lane + (ent >> 7) * 32, 1u << (ent & 31u));
+            delta += 1 - 2 * static_cast<int>((old >> (ent & 31u)) & 1u);
+        }
+    }
+    return delta;
+}
+
 template <int MODE, bool BIG, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_constant__ KernelParams p)
 {
@@ -646,7 +668,20 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 }
                 // Only variables whose decision flipped touch the residual syndrome s xor H*e
                 // (syndrome re-check :180-181, kept incrementally; lanes walk their own flips).
-                if (flips) apply_flips(flips, 0);
+                if (flips) {
+                    if (p.uni_vdeg) {
+                        uint32_t *rl = resid + lane;
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        delta += flip_walk_uniform<D>(static_cast<uint32_t>(flips), 0, warp, W, vflip_at, rl);   \
+        if (flips >> 32) delta += flip_walk_uniform<D>(static_cast<uint32_t>(flips >> 32), 32, warp, W, vflip_at, rl); \
+    }
+                        BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
+#undef BP_CASE
+                    } else {
+                        apply_flips(flips, 0);
+                    }
+                }
                 if (delta) atomicAdd(nnz + par * 32 + lane, delta);
             }
         }
