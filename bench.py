@@ -429,6 +429,42 @@ def main():
                       (info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12)})
         line["sweep"] = sweep
 
+    # ---- config C2 of BASELINE.json next to the headline (1 M syndromes, per sweep), N = 1 only
+    if world == 1 and not args.no_sweep and args.workload == "C3":
+        H2, _, mi2 = pkg.codes.config_matrix("C2")
+        B2 = 1_000_000
+        c2 = []
+        for p_ in (0.001, 0.01, 0.03, 0.1):
+            d2 = pkg.BeliefPropagationDecoder(H2, p_, mi2, devices=[local])
+            i2 = d2.info()
+            t2 = torch.empty((B2, i2["err_words"]), dtype=torch.int32, device=dev)
+            s2 = torch.empty((B2, i2["syn_words"]), dtype=torch.int32, device=dev)
+            e2 = torch.empty((B2, i2["err_words"]), dtype=torch.int32, device=dev)
+            cv2 = torch.empty(B2, dtype=torch.uint8, device=dev)
+            c4 = torch.zeros(4, dtype=torch.int64, device=dev)
+            d2.sample_device(B2, 0, SEED_E, p_, t2.data_ptr(), s2.data_ptr(), stream=st)
+            for _ in range(3):
+                d2.decode_device(B2, s2.data_ptr(), e2.data_ptr(), cv2.data_ptr(), None, None, None, stream=st)
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            ea.record(stream)
+            for _ in range(reps):
+                if flush is not None:
+                    pass
+                d2.decode_device(B2, s2.data_ptr(), e2.data_ptr(), cv2.data_ptr(), None, None, c4.data_ptr(), stream=st)
+            eb.record(stream)
+            torch.cuda.synchronize()
+            secs2 = ea.elapsed_time(eb) / 1e3
+            cc = c4.cpu().numpy()
+            c2.append({"per": p_, "value": float(cc[0]) / secs2, "mean_iters": float(cc[2]) / float(cc[0]),
+                       "converged_frac": float(cc[1]) / float(cc[0]), "syndrome_iterations_per_s": float(cc[2]) / secs2,
+                       "fp64_frac": float(cc[2]) / secs2 * H2.nnz * FP64_SLOTS_PER_EDGE_ITER / 1e12 /
+                       (info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12)})
+            d2.close()
+            del t2, s2, e2, cv2
+        line["config_C2_surface_d15_1M"] = c2
+
     # ---- CPU baseline next to it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
         oracle = entry.load_oracle()

@@ -38,11 +38,17 @@
 
 #include "bp_math.cuh"
 
-#ifndef BP_PIPELINE_VARS
-#define BP_PIPELINE_VARS 0
-#endif
-
 namespace bp {
+
+// Node order inside the kernels is degree-sorted (host: build_graph): nodes of equal degree form
+// contiguous segments [first, end) so the degree dispatch happens once per segment, and slot /
+// table addresses inside a segment are affine in the node index.
+constexpr int kMaxSeg = 8;
+struct Segments {
+    int ncseg, nvseg;                                 // 0 = too many distinct degrees: per-node path
+    int cdeg[kMaxSeg], cfirst[kMaxSeg], cend[kMaxSeg], cslot[kMaxSeg];   // cslot = first message slot of the segment
+    int vdeg[kMaxSeg], vfirst[kMaxSeg], vend[kMaxSeg], vedge[kMaxSeg];   // vedge = first edge-table entry of the segment
+};
 
 struct KernelParams {
     int s, n, E;
@@ -63,7 +69,11 @@ struct KernelParams {
     const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
     int tables_bytes;             // multiple of 16
     int off_colptr, off_ve, off_vflip;   // byte offsets inside the blob (rowptr at 0)
+    int off_corig, off_vorig;            // u16 original ids of the kernels' check / variable order (if permuted)
+    int perm_c, perm_v;                  // node order differs from the caller's (degree-sorted)
+    Segments seg;
     // wide tables (mode 2), read from global memory:
+    const int *g_corig, *g_vorig;        // [s], [n] original ids
     const int *g_rowptr, *g_colptr;      // [s+1], [n+1]
     const uint32_t *g_ve_off;            // [E] slot * 256
     const uint32_t *g_vflip;             // [E] (check/32)*128 + check%32
@@ -284,7 +294,6 @@ template <int MODE, bool BIG, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_constant__ KernelParams p)
 {
     constexpr bool kMsgShared = MODE == 0;
-    constexpr bool kPipelineVars = BP_PIPELINE_VARS != 0;
     constexpr bool kStateShared = MODE <= 1;
     using MH = typename std::conditional<kMsgShared, uint32_t, unsigned char *>::type;   // message column handle
     using TH = typename std::conditional<kStateShared, uint32_t, const uint32_t *>::type;  // slot-offset table handle
@@ -343,7 +352,24 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
         if constexpr (kStateShared) return ve_a + 4 * e;
         else return p.g_ve_off + e;
     };
-    auto syn_bit = [&](int i) -> bool {
+    const uint32_t corig_a = sbase + p.off_tables + p.off_corig;
+    const uint32_t vorig_a = sbase + p.off_tables + p.off_vorig;
+    auto corig_at = [&](int i) -> int {               // original index of the kernels' i-th check
+        if (!p.perm_c) return i;
+        if constexpr (kStateShared) return static_cast<int>(lds_u16(corig_a + 2 * i));
+        else return __ldg(p.g_corig + i);
+    };
+    auto vorig_at = [&](int j) -> int {
+        if (!p.perm_v) return j;
+        if constexpr (kStateShared) return static_cast<int>(lds_u16(vorig_a + 2 * j));
+        else return __ldg(p.g_vorig + j);
+    };
+    auto syn_bit_direct = [&](int i) -> bool {        // syndrome bit of original check i
+        if constexpr (kStateShared) return (lds_u32(syn_a + (i >> 5) * 128) >> (i & 31)) & 1u;
+        else return (syn[(i >> 5) * 32 + lane] >> (i & 31)) & 1u;
+    };
+    auto syn_bit = [&](int ik) -> bool {              // syndrome bit of the kernels' ik-th check
+        const int i = corig_at(ik);
         if constexpr (kStateShared) return (lds_u32(syn_a + (i >> 5) * 128) >> (i & 31)) & 1u;
         else return (syn[(i >> 5) * 32 + lane] >> (i & 31)) & 1u;
     };
@@ -481,14 +507,38 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             }
         } else if (active) {
             if (p.uni_cdeg) {
-                // every check has the same degree: slots of check i start at i*D, no table reads
+                // every check has the same degree (and the node order is the caller's): slots of
+                // check i start at i*D, no table or segment reads
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         MH a = ml + warp * (D * 256);                                                            \
-        for (int i = warp; i < p.s; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit(i), fresh, p0); \
+        for (int i = warp; i < p.s; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0); \
     }
                 BP_DEGREE_SWITCH(p.uni_cdeg, BP_CASE, ;)
 #undef BP_CASE
+            } else if (p.seg.ncseg > 0) {
+                // segments of equal degree: slots of the segment's u-th check start at cslot + u*D
+                int i = warp;
+                for (int g = 0; g < p.seg.ncseg; ++g) {
+                    const int deg = p.seg.cdeg[g], first = p.seg.cfirst[g], end = p.seg.cend[g], sb = p.seg.cslot[g];
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        MH a = ml + (sb + (i - first) * D) * 256;                                                \
+        if (p.perm_c)                                                                            \
+            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit(i), fresh, p0); \
+        else                                                                                     \
+            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0); \
+    }
+                    BP_DEGREE_SWITCH(
+                        deg, BP_CASE, if (BIG) {
+                            for (; i < end; i += W) {
+                                double *base = reinterpret_cast<double *>(msg_generic + static_cast<size_t>(sb + (i - first) * deg) * 256);
+                                check_update_big([&](int k) -> double & { return base[k * 32]; }, deg, syn_bit(i), fresh, p0);
+                            }
+                        })
+#undef BP_CASE
+                    if (deg == 0) i += ((end - i + W - 1) / W) * W;   // isolated checks: nothing to send
+                }
             } else {
                 for (int i = warp; i < p.s; i += W) {
                     const int rp = rowptr_at(i);
@@ -528,7 +578,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             };
             // posterior ratio R of this lane's i-th variable j: optional output, hard decision (:163-168)
             auto record = [&](int j, int i, double R) {
-                if (p.ratio) p.ratio[sid * p.n + j] = R;
+                if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
                 const uint32_t bit = (R >= 1.0) ? 1u : 0u;                            // tie -> 1
                 if (use_regs) {
                     newbits |= static_cast<unsigned long long>(bit) << i;
@@ -601,31 +651,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 }
             } else if (active) {
                 if (p.uni_vdeg && use_regs) {
-                    // low degrees are software-pipelined: the next variable's slot offsets and
-                    // messages are fetched while the current one is being multiplied out
 #define BP_CASE(D)                                                                               \
-    if constexpr (D <= 4 && kPipelineVars) {                                                     \
-        TH vea = ve_handle(warp * D);                                                            \
-        uint32_t v[D], vn[D];                                                                    \
-        double m[D], mn[D];                                                                      \
-        if (warp < p.n) {                                                                        \
-            load_offsets<D>(v, vea);                                                             \
-            _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = ld_msg(ml + v[k]);              \
-        }                                                                                        \
-        int i = 0;                                                                               \
-        for (int j = warp; j < p.n; j += W, ++i) {                                               \
-            vea += W * D * (kStateShared ? 4 : 1);                                               \
-            if (j + W < p.n) {                                                                   \
-                load_offsets<D>(vn, vea);                                                        \
-                _Pragma("unroll") for (int k = 0; k < D; ++k) mn[k] = ld_msg(ml + vn[k]);        \
-            }                                                                                    \
-            const double R = var_update<D>(m, p0, regular_p0);                                   \
-            _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);               \
-            if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
-            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
-            _Pragma("unroll") for (int k = 0; k < D; ++k) { v[k] = vn[k]; m[k] = mn[k]; }        \
-        }                                                                                        \
-    } else {                                                                                     \
+    {                                                                                            \
         TH vea = ve_handle(warp * D);                                                            \
         int i = 0;                                                                               \
         for (int j = warp; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {        \
@@ -636,6 +663,44 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     }
                     BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
 #undef BP_CASE
+                } else if (p.seg.nvseg > 0 && use_regs) {
+                    int j = warp, i = 0;
+                    for (int g = 0; g < p.seg.nvseg; ++g) {
+                        const int deg = p.seg.vdeg[g], first = p.seg.vfirst[g], end = p.seg.vend[g], eb = p.seg.vedge[g];
+                        if (deg == 0) {                                               // isolated variables: prior only
+                            for (; j < end; j += W, ++i) {
+                                if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = p0;
+                                newbits |= static_cast<unsigned long long>((p0 >= 1.0) ? 1u : 0u) << i;
+                            }
+                            continue;
+                        }
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        TH vea = ve_handle(eb + (j - first) * D);                                                \
+        for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
+            const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
+            if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;                                   \
+            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
+        }                                                                                        \
+    }
+                        BP_DEGREE_SWITCH(
+                            deg, BP_CASE, if (BIG) {
+                                for (; j < end; j += W, ++i) {
+                                    const int cp = eb + (j - first) * deg;
+                                    const double R = var_update_big(
+                                        [&](int k) -> double & {
+                                            uint32_t off;
+                                            if constexpr (kStateShared) off = lds_u32(ve_a + 4 * (cp + k));
+                                            else off = __ldg(p.g_ve_off + cp + k);
+                                            return *reinterpret_cast<double *>(msg_generic + off);
+                                        },
+                                        deg, p0);
+                                    if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
+                                    newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;
+                                }
+                            })
+#undef BP_CASE
+                    }
                 } else {
                     // general degrees and/or more than 64 variables per warp (decision fields in memory)
                     int i = 0;
@@ -697,7 +762,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             // pre-zeroed packed row
             auto emit = [&](unsigned long long b, int ibase) {
                 while (b) {
-                    const int j = warp + (ibase + __ffsll(static_cast<long long>(b)) - 1) * W;
+                    const int j = vorig_at(warp + (ibase + __ffsll(static_cast<long long>(b)) - 1) * W);
                     b &= b - 1;
                     atomicOr(p.err_words + sid * p.NW + (j >> 5), 1u << (j & 31));
                 }

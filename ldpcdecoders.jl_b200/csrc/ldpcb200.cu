@@ -75,7 +75,9 @@ struct DeviceCtx {
     // graph tables
     int *d_rowptr = nullptr, *d_colptr = nullptr, *d_ve_slot = nullptr, *d_ve_chk = nullptr;
     unsigned char *d_tables = nullptr;
-    uint32_t *d_ve_off = nullptr, *d_vflip = nullptr;   // wide tables (mode 2)
+    // decoder tables in the kernels' node order (mode 2 reads them from global memory)
+    int *d_p_rowptr = nullptr, *d_p_colptr = nullptr, *d_corig = nullptr, *d_vorig = nullptr;
+    uint32_t *d_ve_off = nullptr, *d_vflip = nullptr;
     // family GLOBAL stores: per resident CTA messages (+ syndrome state / decision fields when those are global)
     DevBuf msg, state, efield;
     // host-batch staging: two buffer sets / streams so that the copies of one chunk overlap the
@@ -99,9 +101,13 @@ struct ldpcb200 {
     int uni_cdeg = 0, uni_vdeg = 0;   // common degree when every check / variable has the same one (<= 12)
     bool big = false;
     int SW = 0, NW = 0;
-    std::vector<int> rowptr, colptr, ve_slot, ve_chk;
+    std::vector<int> rowptr, colptr, ve_slot, ve_chk;      // original node order (sampler / scorer)
+    // decoder tables in degree-sorted node order (kernels); corig/vorig map back to original ids
+    std::vector<int> p_rowptr, p_colptr, p_ve_slot, p_ve_chk, corig, vorig;
+    bool perm_c = false, perm_v = false;
+    bp::Segments segs{};
     std::vector<unsigned char> tables;   // SMEM-family blob
-    int off_colptr = 0, off_ve = 0, off_vflip = 0;
+    int off_colptr = 0, off_ve = 0, off_vflip = 0, off_corig = 0, off_vorig = 0;
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
@@ -202,27 +208,109 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
     h->NW = static_cast<int>((n + 31) / 32);
     if (h->SW == 0) h->SW = 1;
     if (h->NW == 0) h->NW = 1;
+    // ---- degree-sorted node order for the kernels: nodes of equal degree become contiguous
+    // "segments", so the per-node degree switch and table reads are hoisted out of the node
+    // loops.  Inside a node the edge order stays ascending in ORIGINAL indices (the order the
+    // reference multiplies in); corig/vorig translate syndrome bits and output positions.
+    {
+        std::vector<int> cdeg(s), vdeg(n);
+        for (int64_t i = 0; i < s; ++i) cdeg[i] = h->rowptr[i + 1] - h->rowptr[i];
+        for (int64_t j = 0; j < n; ++j) vdeg[j] = h->colptr[j + 1] - h->colptr[j];
+        h->corig.resize(s); h->vorig.resize(n);
+        for (int64_t i = 0; i < s; ++i) h->corig[i] = static_cast<int>(i);
+        for (int64_t j = 0; j < n; ++j) h->vorig[j] = static_cast<int>(j);
+        std::stable_sort(h->corig.begin(), h->corig.end(), [&](int a, int b) { return cdeg[a] < cdeg[b]; });
+        std::stable_sort(h->vorig.begin(), h->vorig.end(), [&](int a, int b) { return vdeg[a] < vdeg[b]; });
+        auto count_runs = [](const std::vector<int> &order, const std::vector<int> &deg) {
+            int runs = 0;
+            for (size_t k = 0; k < order.size(); ++k) runs += (k == 0 || deg[order[k]] != deg[order[k - 1]]);
+            return runs;
+        };
+        // codes with many distinct degrees keep the original order and the per-node path
+        if (count_runs(h->corig, cdeg) > bp::kMaxSeg) for (int64_t i = 0; i < s; ++i) h->corig[i] = static_cast<int>(i);
+        if (count_runs(h->vorig, vdeg) > bp::kMaxSeg) for (int64_t j = 0; j < n; ++j) h->vorig[j] = static_cast<int>(j);
+        h->perm_c = h->perm_v = false;
+        for (int64_t i = 0; i < s; ++i) h->perm_c |= h->corig[i] != i;
+        for (int64_t j = 0; j < n; ++j) h->perm_v |= h->vorig[j] != j;
+        std::vector<int> inv_c(s);
+        for (int64_t i = 0; i < s; ++i) inv_c[h->corig[i]] = static_cast<int>(i);
+        h->p_rowptr.assign(s + 1, 0);
+        for (int64_t i = 0; i < s; ++i) h->p_rowptr[i + 1] = h->p_rowptr[i] + cdeg[h->corig[i]];
+        // slot of every original CSC edge: columns visited in ascending original order => inside a
+        // check, variables ascend in original index (nzrange(sparse_HT, i), belief_propagation.jl:137)
+        std::vector<int> slot_of(std::max<int64_t>(E, 1), 0), fill2(s);
+        for (int64_t r = 0; r < s; ++r) fill2[r] = h->p_rowptr[inv_c[r]];
+        for (int64_t j = 0; j < n; ++j)
+            for (int e = h->colptr[j]; e < h->colptr[j + 1]; ++e) slot_of[e] = fill2[h->ve_chk[e]]++;
+        h->p_colptr.assign(n + 1, 0);
+        h->p_ve_slot.assign(std::max<int64_t>(E, 1), 0);
+        h->p_ve_chk.assign(std::max<int64_t>(E, 1), 0);
+        for (int64_t jp = 0; jp < n; ++jp) {
+            const int j = h->vorig[jp];
+            h->p_colptr[jp + 1] = h->p_colptr[jp] + vdeg[j];
+            for (int k = 0; k < vdeg[j]; ++k) {      // ascending original check index (:155)
+                h->p_ve_slot[h->p_colptr[jp] + k] = slot_of[h->colptr[j] + k];
+                h->p_ve_chk[h->p_colptr[jp] + k] = h->ve_chk[h->colptr[j] + k];
+            }
+        }
+        // segments (only used when they cover the node order with <= kMaxSeg runs)
+        bp::Segments &sg = h->segs;
+        sg.ncseg = sg.nvseg = 0;
+        if (count_runs(h->corig, cdeg) <= bp::kMaxSeg && s > 0) {
+            for (int64_t i = 0; i < s; ++i) {
+                const int dg = cdeg[h->corig[i]];
+                if (i == 0 || dg != sg.cdeg[sg.ncseg - 1]) {
+                    sg.cdeg[sg.ncseg] = dg; sg.cfirst[sg.ncseg] = static_cast<int>(i); sg.cslot[sg.ncseg] = h->p_rowptr[i];
+                    ++sg.ncseg;
+                }
+                sg.cend[sg.ncseg - 1] = static_cast<int>(i + 1);
+            }
+        }
+        if (count_runs(h->vorig, vdeg) <= bp::kMaxSeg && n > 0) {
+            for (int64_t j = 0; j < n; ++j) {
+                const int dg = vdeg[h->vorig[j]];
+                if (j == 0 || dg != sg.vdeg[sg.nvseg - 1]) {
+                    sg.vdeg[sg.nvseg] = dg; sg.vfirst[sg.nvseg] = static_cast<int>(j); sg.vedge[sg.nvseg] = h->p_colptr[j];
+                    ++sg.nvseg;
+                }
+                sg.vend[sg.nvseg - 1] = static_cast<int>(j + 1);
+            }
+        }
+    }
     // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes) | vflip u16[E]
+    //                   | corig u16[s] | vorig u16[n]      (all in the kernels' node order)
     if (E <= 0xffff && s <= 16384 && n <= 0xffff) {
         const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
         const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
         const int o_fl = o_ve + static_cast<int>(4 * E);
-        const int total = align_up(o_fl + static_cast<int>(2 * E), 16);
+        const int o_co = align_up(o_fl + static_cast<int>(2 * E), 4);
+        const int o_vo = o_co + (h->perm_c ? static_cast<int>(2 * s) : 0);
+        const int total = align_up(o_vo + (h->perm_v ? static_cast<int>(2 * n) : 0), 16);
         h->tables.assign(std::max(total, 16), 0);
         uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
         uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
         uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
-        for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->rowptr[i]);
-        for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->colptr[j]);
+        for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->p_rowptr[i]);
+        for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->p_colptr[j]);
         uint16_t *fl = reinterpret_cast<uint16_t *>(h->tables.data() + o_fl);
         for (int64_t e = 0; e < E; ++e) {
-            ve[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
+            ve[e] = static_cast<uint32_t>(h->p_ve_slot[e]) * 256u;
             // residual-syndrome word (byte offset of its 128 B row) | bit: needs s <= 16384
-            fl[e] = static_cast<uint16_t>((h->ve_chk[e] >> 5) * 128 + (h->ve_chk[e] & 31));
+            fl[e] = static_cast<uint16_t>((h->p_ve_chk[e] >> 5) * 128 + (h->p_ve_chk[e] & 31));
+        }
+        if (h->perm_c) {
+            uint16_t *co = reinterpret_cast<uint16_t *>(h->tables.data() + o_co);
+            for (int64_t i = 0; i < s; ++i) co[i] = static_cast<uint16_t>(h->corig[i]);
+        }
+        if (h->perm_v) {
+            uint16_t *vo = reinterpret_cast<uint16_t *>(h->tables.data() + o_vo);
+            for (int64_t j = 0; j < n; ++j) vo[j] = static_cast<uint16_t>(h->vorig[j]);
         }
         h->off_colptr = o_col;
         h->off_ve = o_ve;
         h->off_vflip = o_fl;
+        h->off_corig = o_co;
+        h->off_vorig = o_vo;
     }
     return 0;
 }
@@ -256,11 +344,15 @@ int init_device(ldpcb200 *h, DeviceCtx &d)
         CU(cudaMalloc(&d.d_tables, h->tables.size()));
         CU(cudaMemcpy(d.d_tables, h->tables.data(), h->tables.size(), cudaMemcpyHostToDevice));
     }
-    {   // wide tables: slot byte offsets and residual (word, bit) of every CSC edge
-        std::vector<uint32_t> off(h->ve_slot.size()), fl(h->ve_slot.size());
+    if ((rc = up(&d.d_p_rowptr, h->p_rowptr))) return rc;
+    if ((rc = up(&d.d_p_colptr, h->p_colptr))) return rc;
+    if (!h->corig.empty() && (rc = up(&d.d_corig, h->corig))) return rc;
+    if (!h->vorig.empty() && (rc = up(&d.d_vorig, h->vorig))) return rc;
+    {   // wide tables: slot byte offsets and residual (word, bit) of every edge, kernels' node order
+        std::vector<uint32_t> off(h->p_ve_slot.size()), fl(h->p_ve_slot.size());
         for (size_t e = 0; e < off.size(); ++e) {
-            off[e] = static_cast<uint32_t>(h->ve_slot[e]) * 256u;
-            fl[e] = static_cast<uint32_t>((h->ve_chk[e] >> 5) * 128 + (h->ve_chk[e] & 31));
+            off[e] = static_cast<uint32_t>(h->p_ve_slot[e]) * 256u;
+            fl[e] = static_cast<uint32_t>((h->p_ve_chk[e] >> 5) * 128 + (h->p_ve_chk[e] & 31));
         }
         CU(cudaMalloc(&d.d_ve_off, sizeof(uint32_t) * off.size()));
         CU(cudaMemcpy(d.d_ve_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
@@ -276,6 +368,7 @@ void destroy_device(DeviceCtx &d)
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_rowptr); cudaFree(d.d_colptr); cudaFree(d.d_ve_slot); cudaFree(d.d_ve_chk);
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
+    cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
     for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch}) b->release();
     for (auto &S : d.set)
@@ -479,7 +572,10 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     p.counters = counters;
     p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
     p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
-    p.g_rowptr = d.d_rowptr; p.g_colptr = d.d_colptr; p.g_ve_off = d.d_ve_off; p.g_vflip = d.d_vflip;
+    p.g_rowptr = d.d_p_rowptr; p.g_colptr = d.d_p_colptr; p.g_ve_off = d.d_ve_off; p.g_vflip = d.d_vflip;
+    p.g_corig = d.d_corig; p.g_vorig = d.d_vorig;
+    p.perm_c = h->perm_c; p.perm_v = h->perm_v; p.off_corig = h->off_corig; p.off_vorig = h->off_vorig;
+    p.seg = h->segs;
     p.nfw = h->nfw;
     int rc;
     if (h->mode >= 1) {
