@@ -459,6 +459,54 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             // next pd checks into a shared-memory ring with 16-byte cp.async.cg copies (two 256 B rows
             // per instruction), so pd nodes' worth of loads are always in flight per warp.
             if constexpr (!kMsgShared) {
+              if (p.seg.ncseg > 0) {
+                // degree segments: compile-time degree, affine row addresses, the copy loop unrolled
+                const int nslot = p.pd + 1;
+                const uint32_t ring_c = sbase + p.off_ring + warp * p.ring_warp_bytes + (lane & 15) * 16;   // copy view
+                const uint32_t ring_l = sbase + p.off_ring + warp * p.ring_warp_bytes + lane * 8;           // lane view
+                unsigned char *cta_msg = msg_generic - lane * 8;
+                int i = warp;
+                for (int g = 0; g < p.seg.ncseg; ++g) {
+                    const int deg = p.seg.cdeg[g], first = p.seg.cfirst[g], end = p.seg.cend[g], sb = p.seg.cslot[g];
+                    if (deg == 0) { if (i < end) i += ((end - i + W - 1) / W) * W; continue; }
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        const unsigned char *isrc = cta_msg + static_cast<size_t>(sb + (i - first) * D) * 256 + (lane & 15) * 16; \
+        unsigned char *ga = msg_generic + static_cast<size_t>(sb + (i - first) * D) * 256;       \
+        int ii = i, islot = 0, cslot = 0;                                                        \
+        auto issue = [&]() {                                                                     \
+            if (ii < end) {                                                                      \
+                _Pragma("unroll") for (int k = 0; k < D; k += 2)                                 \
+                    if (k + (lane >> 4) < D)                                                     \
+                        cp_async16(ring_c + islot * p.ring_slot_bytes + (k + (lane >> 4)) * 256, isrc + (k + (lane >> 4)) * 256); \
+            }                                                                                    \
+            cp_async_commit();                                                                   \
+            ii += W; isrc += static_cast<size_t>(W) * (D * 256);                                 \
+            islot = (islot + 1 == nslot) ? 0 : islot + 1;                                        \
+        };                                                                                       \
+        for (int t = 0; t < p.pd; ++t) issue();                                                  \
+        for (; i < end; i += W, ga += static_cast<size_t>(W) * (D * 256)) {                      \
+            issue();                                                                             \
+            cp_async_wait_pending(p.pd);                                                         \
+            __syncwarp();                                                                        \
+            if (active) check_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, ga, syn_bit(i), fresh, p0); \
+            __syncwarp();                                                                        \
+            cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                        \
+        }                                                                                        \
+        cp_async_wait_all();                                                                     \
+    }
+                    BP_DEGREE_SWITCH(
+                        deg, BP_CASE, if (BIG) {
+                            for (; i < end; i += W) {
+                                if (active) {
+                                    double *base = reinterpret_cast<double *>(msg_generic + static_cast<size_t>(sb + (i - first) * deg) * 256);
+                                    check_update_big([&](int k) -> double & { return base[k * 32]; }, deg, syn_bit(i), fresh, p0);
+                                }
+                            }
+                        })
+#undef BP_CASE
+                }
+              } else {
                 const int nslot = p.pd + 1;
                 const uint32_t ring_w = sbase + p.off_ring + warp * p.ring_warp_bytes;
                 unsigned char *cta_msg = msg_generic - lane * 8;
@@ -504,6 +552,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                     cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;
                 }
                 cp_async_wait_all();
+              }
             }
         } else if (active) {
             if (p.uni_cdeg) {
@@ -597,6 +646,62 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             };
             if (staged) {
                 if constexpr (!kMsgShared) {
+                  if (p.seg.nvseg > 0) {
+                    const int nslot = p.pd + 1;
+                    const uint32_t ring_c = sbase + p.off_ring + warp * p.ring_warp_bytes + (lane & 15) * 16;
+                    const uint32_t ring_l = sbase + p.off_ring + warp * p.ring_warp_bytes + lane * 8;
+                    unsigned char *cta_msg = msg_generic - lane * 8 + (lane & 15) * 16;
+                    auto off_at = [&](int e) -> uint32_t {
+                        if constexpr (kStateShared) return lds_u32(ve_a + 4 * e);
+                        else return __ldg(p.g_ve_off + e);
+                    };
+                    int j = warp, i = 0;
+                    for (int g = 0; g < p.seg.nvseg; ++g) {
+                        const int deg = p.seg.vdeg[g], first = p.seg.vfirst[g], end = p.seg.vend[g], eb = p.seg.vedge[g];
+                        if (deg == 0) {
+                            for (; j < end; j += W, ++i)
+                                if (active) record(j, i, p0);
+                            continue;
+                        }
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        int jj = j, ie = eb + (j - first) * D, islot = 0, cslot = 0;                             \
+        auto issue = [&]() {                                                                     \
+            if (jj < end) {                                                                      \
+                _Pragma("unroll") for (int k = 0; k < D; k += 2)                                 \
+                    if (k + (lane >> 4) < D)                                                     \
+                        cp_async16(ring_c + islot * p.ring_slot_bytes + (k + (lane >> 4)) * 256, cta_msg + off_at(ie + k + (lane >> 4))); \
+            }                                                                                    \
+            cp_async_commit();                                                                   \
+            jj += W; ie += W * D;                                                                \
+            islot = (islot + 1 == nslot) ? 0 : islot + 1;                                        \
+        };                                                                                       \
+        for (int t = 0; t < p.pd; ++t) issue();                                                  \
+        TH vea = ve_handle(eb + (j - first) * D);                                                \
+        for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
+            issue();                                                                             \
+            cp_async_wait_pending(p.pd);                                                         \
+            __syncwarp();                                                                        \
+            if (active) record(j, i, var_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, msg_generic, vea, p0, regular_p0)); \
+            __syncwarp();                                                                        \
+            cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                        \
+        }                                                                                        \
+        cp_async_wait_all();                                                                     \
+    }
+                        BP_DEGREE_SWITCH(
+                            deg, BP_CASE, if (BIG) {
+                                for (; j < end; j += W, ++i) {
+                                    if (active) {
+                                        const int cp = eb + (j - first) * deg;
+                                        record(j, i, var_update_big(
+                                            [&](int k) -> double & { return *reinterpret_cast<double *>(msg_generic + off_at(cp + k)); },
+                                            deg, p0));
+                                    }
+                                }
+                            })
+#undef BP_CASE
+                    }
+                  } else {
                     const int nslot = p.pd + 1;
                     const uint32_t ring_w = sbase + p.off_ring + warp * p.ring_warp_bytes;
                     unsigned char *cta_msg = msg_generic - lane * 8;
@@ -648,6 +753,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                         cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;
                     }
                     cp_async_wait_all();
+                  }
                 }
             } else if (active) {
                 if (p.uni_vdeg && use_regs) {
