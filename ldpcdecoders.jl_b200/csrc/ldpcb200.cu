@@ -499,26 +499,40 @@ int configure(ldpcb200 *h)
     // ---- family GLOBAL: messages in HBM/L2; state + tables in shared memory (mode 1) if they fit, else global (mode 2)
     if (mode < 0) {
         family = LDPCB200_FAMILY_GLOBAL;
-        const int wmax = 12;
-        warps = h->opt_warps > 0 ? std::min(h->opt_warps, 16) : pick_warps(h->s, h->n, 8, wmax);
-        two = warps <= 12;
-        nfw = fields(warps);
         const int pd_max = h->opt_pd >= 0 ? std::min(h->opt_pd, 3) : 3;
-        const int budget = two ? per_cta_2 : d0.smem_optin;
-        if (narrow) {
-            const long long ef_bytes = static_cast<long long>(nfw) * warps * 32 * 4;
-            const bool ef_smem = ef_bytes <= 32 * 1024;
-            for (int pd = pd_max; pd >= 0 && mode < 0; --pd) {
-                need = smem_layout(h, 1, warps * 32, nfw, ef_smem, pd, kp);
-                if (need <= budget) { mode = 1; ef_global = nfw > 0 && !ef_smem; }
+        // HBM-bound: the depth of the cp.async ring matters more than the warp count, so take the
+        // widest CTA (12, 10, 8 warps; two CTAs per SM) whose ring still reaches the full depth,
+        // else the one with the deepest ring.  mode 1 (state + tables in shared memory) if it fits.
+        std::vector<int> cand;
+        if (h->opt_warps > 0) cand.push_back(std::min(h->opt_warps, 16));
+        else cand = {12, 10, 8};
+        int best_pd = -1;
+        for (int w : cand) {
+            const bool two_w = w <= 12;
+            const int budget = two_w ? per_cta_2 : d0.smem_optin;
+            const int f = fields(w);
+            int m = -1, pd_fit = -1, need_w = 0;
+            bool efg = false;
+            bp::KernelParams kw{};
+            if (narrow) {
+                const long long ef_bytes = static_cast<long long>(f) * w * 32 * 4;
+                const bool ef_smem = ef_bytes <= 32 * 1024;
+                for (int pd = pd_max; pd >= 0 && m < 0; --pd) {
+                    need_w = smem_layout(h, 1, w * 32, f, ef_smem, pd, kw);
+                    if (need_w <= budget) { m = 1; pd_fit = pd; efg = f > 0 && !ef_smem; }
+                }
             }
-        }
-        if (mode < 0) {
-            for (int pd = pd_max; pd >= 0 && mode < 0; --pd) {
-                need = smem_layout(h, 2, warps * 32, nfw, false, pd, kp);
-                if (need <= budget) mode = 2;
+            if (m < 0) {
+                for (int pd = pd_max; pd >= 0 && m < 0; --pd) {
+                    need_w = smem_layout(h, 2, w * 32, f, false, pd, kw);
+                    if (need_w <= budget) { m = 2; pd_fit = pd; }
+                }
+                efg = f > 0;
             }
-            ef_global = nfw > 0;
+            if (m >= 0 && pd_fit > best_pd) {
+                best_pd = pd_fit; mode = m; warps = w; two = two_w; nfw = f; need = need_w; ef_global = efg; kp = kw;
+            }
+            if (best_pd == pd_max) break;
         }
         if (mode < 0) return fail(LDPCB200_EUNSUPPORTED, "no kernel configuration fits in shared memory");
     }
