@@ -388,11 +388,18 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
         const long long sid = (((q >> 5) * G + c) << 5) + (q & 31);
         return (q < Q && sid < p.B) ? sid : -1;
     };
-    auto prefetch = [&](long long q_head) {      // warp 0: stage[w][r] <- syndrome words of entry q_head + r
+    // Bookkeeping of the done-detection phase is spread over three warps so that no single warp
+    // holds the others up at the barrier: wS moves staged syndromes into slots, wP prefetches the
+    // next queue window (double-buffered stage, so it may overwrite while wS still reads), wO
+    // writes converged flags / iteration counts and keeps the counters.
+    const int wS = 0, wP = (W > 1) ? 1 : 0, wO = (W > 2) ? 2 : 0;
+    int sbuf = 0;                                 // stage buffer the next refill reads
+    auto prefetch = [&](long long q_head, int buf) {      // stage[buf][w][r] <- syndrome words of entry q_head + r
         if constexpr (kStateShared) {
             const long long sid = sid_of(q_head + lane);
             if (sid >= 0)
-                for (int w = 0; w < p.SW; ++w) cp_async4(&stage[w * 32 + lane], p.syn_words + sid * p.SW + w);
+                for (int w = 0; w < p.SW; ++w)
+                    cp_async4(&stage[(buf * p.SW + w) * 32 + lane], p.syn_words + sid * p.SW + w);
         }
     };
 
@@ -404,18 +411,16 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     // Hard decisions of the variables this warp owns (j = warp + i*W  <->  bit i), one bit set per
     // variable currently decided 1 (codes with at most 64 variables per warp; else `efield`).
     unsigned long long ebits = 0;
-    unsigned long long n_done = 0, n_conv = 0, n_iters = 0;   // warp 0 only
+    unsigned long long n_done = 0, n_conv = 0, n_iters = 0;   // warp wO only
 
-    if (warp == 0) prefetch(0);
+    if (warp == wP) { prefetch(0, sbuf); cp_async_wait_all(); }
     __syncthreads();
     if constexpr (kStateShared) mbar_wait(mbar, 0);           // tables have landed
 
     // Lanes in `mask` take the next queue entries.  Executed identically by every warp
-    // (register state is replicated); warp 0 additionally moves the syndrome in.
+    // (register state is replicated); warp wS additionally moves the syndrome in.  The staged
+    // window was completed by wP before the preceding barrier.
     auto refill = [&](uint32_t mask, int nnz_buf) {
-        if constexpr (kStateShared) {
-            if (warp == 0) { cp_async_wait_all(); __syncwarp(); }
-        }
         if ((mask >> lane) & 1u) {
             const int rank = __popc(mask & lt_mask);
             sid = sid_of(q_head + rank);
@@ -425,11 +430,11 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             ebits = 0;                                                      // err .= 0 (reset!, :89)
             if (!use_regs)
                 for (int k = 0; k < p.nfw; ++k) efield[static_cast<size_t>(k) * blockDim.x] = 0u;
-            if (warp == 0 && active) {
+            if (warp == wS && active) {
                 int cnt = 0;
                 for (int w = 0; w < p.SW; ++w) {
                     uint32_t v;
-                    if constexpr (kStateShared) v = stage[w * 32 + rank];
+                    if constexpr (kStateShared) v = stage[(sbuf * p.SW + w) * 32 + rank];
                     else v = p.syn_words[sid * p.SW + w];
                     syn[w * 32 + lane] = v;
                     resid[w * 32 + lane] = v;
@@ -439,9 +444,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             }
         }
         q_head += __popc(mask);
-        if constexpr (kStateShared) {
-            if (warp == 0) { __syncwarp(); prefetch(q_head); }
-        }
+        sbuf ^= 1;
+        if (warp == wP) prefetch(q_head, sbuf);               // lands before the next refill's barrier
     };
 
     refill(0xffffffffu, par);
@@ -856,6 +860,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 if (delta) atomicAdd(nnz + par * 32 + lane, delta);
             }
         }
+        if constexpr (kStateShared) {
+            if (warp == wP) cp_async_wait_all();              // staged window complete before anyone reads it
+        }
         __syncthreads();
         // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)
         const int cur_nnz = nnz[par * 32 + lane];
@@ -877,21 +884,18 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             else
                 for (int k = 0; k < p.nfw; ++k) emit(efield[static_cast<size_t>(k) * blockDim.x], k * 32);
         }
-        if (warp == 0) {
-            if (done) {
-                p.conv[sid] = conv ? 1 : 0;
-                if (p.iters) p.iters[sid] = iter;
-                n_done += 1; n_conv += conv ? 1 : 0; n_iters += iter;
-            } else {
-                nnz[(par ^ 1) * 32 + lane] = cur_nnz;          // carry over to the other buffer
-            }
+        if (warp == wO && done) {
+            p.conv[sid] = conv ? 1 : 0;
+            if (p.iters) p.iters[sid] = iter;
+            n_done += 1; n_conv += conv ? 1 : 0; n_iters += iter;
         }
+        if (warp == wS && !done) nnz[(par ^ 1) * 32 + lane] = cur_nnz;   // carry over to the other buffer
         par ^= 1;
         if (done_mask) refill(done_mask, par);
         __syncthreads();
     }
 
-    if (warp == 0 && p.counters) {
+    if (warp == wO && p.counters) {
         for (int o = 16; o > 0; o >>= 1) {
             n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
             n_conv += __shfl_xor_sync(0xffffffffu, n_conv, o);

@@ -137,7 +137,7 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
     if (mode <= 1) {
         p.off_syn = static_cast<int>(off);    off += h->SW * 128;
         p.off_resid = static_cast<int>(off);  off += h->SW * 128;
-        p.off_stage = static_cast<int>(off);  off += h->SW * 128;
+        p.off_stage = static_cast<int>(off);  off += 2 * h->SW * 128;      // double-buffered
     }
     p.off_nnz = static_cast<int>(off);    off += 2 * 32 * 4;
     p.off_efield = static_cast<int>(off);
