@@ -761,11 +761,30 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 }
             } else if (active) {
                 if (p.uni_vdeg && use_regs) {
+                    // two variables per trip for low degrees: their table and message loads are
+                    // issued together, halving the exposed shared-memory latency per variable
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         TH vea = ve_handle(warp * D);                                                            \
-        int i = 0;                                                                               \
-        for (int j = warp; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {        \
+        int i = 0, j = warp;                                                                     \
+        if constexpr (D <= 4) {                                                                  \
+            const int step = W * D * (kStateShared ? 4 : 1);                                     \
+            for (; j + W < p.n; j += 2 * W, i += 2, vea += 2 * step) {                           \
+                uint32_t va[D], vb[D];                                                           \
+                double ma[D], mb[D];                                                             \
+                load_offsets<D>(va, vea);                                                        \
+                load_offsets<D>(vb, vea + step);                                                 \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) ma[k] = ld_msg(ml + va[k]);        \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) mb[k] = ld_msg(ml + vb[k]);        \
+                const double Ra = var_update<D>(ma, p0, regular_p0);                             \
+                const double Rb = var_update<D>(mb, p0, regular_p0);                             \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
+                if (p.ratio) { p.ratio[sid * p.n + j] = Ra; p.ratio[sid * p.n + j + W] = Rb; }   \
+                newbits |= static_cast<unsigned long long>(((Ra >= 1.0) ? 1u : 0u) | ((Rb >= 1.0) ? 2u : 0u)) << i; \
+            }                                                                                    \
+        }                                                                                        \
+        for (; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
             if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
             newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
