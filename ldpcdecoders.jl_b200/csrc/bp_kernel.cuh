@@ -806,6 +806,26 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         TH vea = ve_handle(eb + (j - first) * D);                                                \
+        if constexpr (D <= 4) {                                                                  \
+            const int step = W * D * (kStateShared ? 4 : 1);                                     \
+            for (; j + W < end; j += 2 * W, i += 2, vea += 2 * step) {                           \
+                uint32_t va[D], vb[D];                                                           \
+                double ma[D], mb[D];                                                             \
+                load_offsets<D>(va, vea);                                                        \
+                load_offsets<D>(vb, vea + step);                                                 \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) ma[k] = ld_msg(ml + va[k]);        \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) mb[k] = ld_msg(ml + vb[k]);        \
+                const double Ra = var_update<D>(ma, p0, regular_p0);                             \
+                const double Rb = var_update<D>(mb, p0, regular_p0);                             \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
+                if (p.ratio) {                                                                   \
+                    p.ratio[sid * p.n + vorig_at(j)] = Ra;                                       \
+                    p.ratio[sid * p.n + vorig_at(j + W)] = Rb;                                   \
+                }                                                                                \
+                newbits |= static_cast<unsigned long long>(((Ra >= 1.0) ? 1u : 0u) | ((Rb >= 1.0) ? 2u : 0u)) << i; \
+            }                                                                                    \
+        }                                                                                        \
         for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
             if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;                                   \
