@@ -37,7 +37,7 @@ def workload_spec(args, pkg):
     H, per, mi = pkg.codes.config_matrix(args.workload)
     default_per = {"C1": 0.01, "C2": 0.01, "C3": 0.03, "C4": 0.02, "C5": 0.02}[args.workload]
     per = args.per if args.per is not None else default_per
-    default_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 16384}[args.workload]
+    default_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 65536}[args.workload]
     B = args.batch if args.batch is not None else default_B
     if args.max_iters is not None:
         mi = args.max_iters

@@ -639,9 +639,13 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
                            static_cast<double>(fmt_bytes(err_fmt, n, err_ld, 2, h->NW) - fmt_bytes(err_fmt, n, err_ld, 1, h->NW)) +
                            (h->SW + h->NW) * 4.0 + 5.0 + (ratio ? 8.0 * n : 0.0);
     // about four chunks per call (every chunk ends with a tail of slow syndromes, so fewer is better, but
-    // at least two are needed to overlap copies with decoding), bounded by 256 MB of staging per set
-    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>((Bd + 3) / 4, 32768);
-    CH = std::min<int64_t>(CH, static_cast<int64_t>(256.0 * 1048576.0 / std::max(per_syn, 1.0)));
+    // at least two are needed to overlap copies with decoding); never less than two waves of the
+    // resident slots (a smaller chunk leaves SMs idle); staging bounded by 256 MB per set, or what
+    // two waves need (<= 2 GB)
+    const double two_waves = 2.0 * h->slots * std::max(per_syn, 1.0);
+    const double budget = std::min(std::max(256.0 * 1048576.0, two_waves), 2048.0 * 1048576.0);
+    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>({(Bd + 3) / 4, 32768, 2 * static_cast<int64_t>(h->slots)});
+    CH = std::min<int64_t>(CH, static_cast<int64_t>(budget / std::max(per_syn, 1.0)));
     CH = std::max<int64_t>(32, (CH + 31) / 32 * 32);
     int rc;
     if ((rc = d.counters.reserve(LDPCB200_NUM_COUNTERS * 8))) return rc;
