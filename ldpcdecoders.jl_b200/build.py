@@ -1,20 +1,25 @@
-"""Build libldpcb200.so in-tree with nvcc for sm_100a (called by __graft_entry__.build())."""
+"""Build libldpcb200.so in-tree with nvcc for sm_100a (called by __graft_entry__.build()).
+
+The persistent kernel is instantiated once per (memory mode, degree path) in its own translation
+unit; the units are compiled in parallel and linked into one shared library."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libldpcb200.so")
-SOURCES = ["ldpcb200.cu"]
-HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "formats.cuh", "../../include/ldpcb200.h"]
+SOURCES = ["ldpcb200.cu"] + ["bp_inst_m%d_b%d.cu" % (m, b) for m in (0, 1, 2) for b in (0, 1)]
+HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "bp_launch.h", "bp_launch_inst.cuh", "formats.cuh", "../../include/ldpcb200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # never contract a*b+c: every FP64 op of the parity path is rounded separately
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
 
@@ -30,20 +35,41 @@ def _stale():
 def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    tmp = LIB + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(SRC_DIR, f) for f in SOURCES]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    pid = os.getpid()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, "%s.%d.o" % (src[:-3], pid))
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(SRC_DIR, src)]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return src, obj, " ".join(cmd), res.returncode, res.stdout
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = []
+    ok = True
+    for src, obj, cmd, rc, out in results:
+        log.append(cmd + "\n" + out)
+        ok &= rc == 0
+    tmp = LIB + ".tmp.%d" % pid
+    if ok:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + [r[1] for r in results]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.append(" ".join(cmd) + "\n" + res.stdout)
+        ok &= res.returncode == 0
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
-    if res.returncode != 0:
+        f.write("\n".join(log))
+    for r in results:
+        if os.path.exists(r[1]):
+            os.remove(r[1])
+    if verbose or not ok:
+        sys.stderr.write("\n".join(log)[-8000:])
+    if not ok:
         raise RuntimeError("nvcc failed (see %s)" % os.path.join(LIB_DIR, "build.log"))
     os.replace(tmp, LIB)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

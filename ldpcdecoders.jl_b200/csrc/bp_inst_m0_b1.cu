@@ -1,0 +1,3 @@
+#define BP_INST_MODE 0
+#define BP_INST_BIG 1
+#include "bp_launch_inst.cuh"

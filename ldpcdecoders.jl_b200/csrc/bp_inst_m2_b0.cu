@@ -1,0 +1,3 @@
+#define BP_INST_MODE 2
+#define BP_INST_BIG 0
+#include "bp_launch_inst.cuh"

@@ -1,0 +1,24 @@
+// bp_launch.h -- launch / occupancy entry points of the persistent kernel, one translation unit
+// per (MODE, BIG) pair so that the instantiations compile in parallel (bp_launch_inst.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bp_kernel.cuh"
+
+namespace bp {
+
+// Launch shapes: (threads <= 256, 2 CTAs/SM, <= 128 regs), (<= 384, 2 CTAs/SM, <= 80 regs; not for
+// the local-memory degree path), (<= 512, 1 CTA/SM, <= 128 regs; mode 0 only).
+enum KernelShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
+
+// Sets the dynamic shared-memory limit and reports resident CTAs per SM.
+cudaError_t kernel_attrs(int mode, bool big, int shape, int smem_bytes, int threads, int *blocks_per_sm);
+void kernel_launch(int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
+
+#define BP_DECLARE_MODE(M, B)                                                                               \
+    cudaError_t kernel_attrs_##M##_##B(int shape, int smem_bytes, int threads, int *blocks_per_sm);       \
+    void kernel_launch_##M##_##B(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
+BP_DECLARE_MODE(0, 0) BP_DECLARE_MODE(0, 1) BP_DECLARE_MODE(1, 0) BP_DECLARE_MODE(1, 1) BP_DECLARE_MODE(2, 0) BP_DECLARE_MODE(2, 1)
+#undef BP_DECLARE_MODE
+
+}  // namespace bp

@@ -1,0 +1,47 @@
+// bp_launch_inst.cuh -- body of one (BP_INST_MODE, BP_INST_BIG) translation unit.
+#include "bp_launch.h"
+
+#define BP_CAT3(a, b, c) a##b##_##c
+#define BP_NAME(prefix, m, b) BP_CAT3(prefix, m, b)
+
+namespace bp {
+
+template <int MAXT, int MINB>
+static cudaError_t attrs_one(int smem_bytes, int threads, int *blocks_per_sm)
+{
+    auto k = bp_persistent_kernel<BP_INST_MODE, BP_INST_BIG != 0, MAXT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (BP_INST_MODE == 0) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes);
+}
+
+cudaError_t BP_NAME(kernel_attrs_, BP_INST_MODE, BP_INST_BIG)(int shape, int smem_bytes, int threads, int *bps)
+{
+    if (shape == kShape256x2) return attrs_one<256, 2>(smem_bytes, threads, bps);
+#if !BP_INST_BIG
+    if (shape == kShape384x2) return attrs_one<384, 2>(smem_bytes, threads, bps);
+#endif
+#if BP_INST_MODE == 0
+    if (shape == kShape512x1) return attrs_one<512, 1>(smem_bytes, threads, bps);
+#endif
+    return cudaErrorInvalidConfiguration;
+}
+
+void BP_NAME(kernel_launch_, BP_INST_MODE, BP_INST_BIG)(int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
+                                                        const KernelParams &p)
+{
+    constexpr bool kBig = BP_INST_BIG != 0;
+    if (shape == kShape256x2) bp_persistent_kernel<BP_INST_MODE, kBig, 256, 2><<<grid, threads, smem_bytes, st>>>(p);
+#if !BP_INST_BIG
+    if (shape == kShape384x2) bp_persistent_kernel<BP_INST_MODE, kBig, 384, 2><<<grid, threads, smem_bytes, st>>>(p);
+#endif
+#if BP_INST_MODE == 0
+    if (shape == kShape512x1) bp_persistent_kernel<BP_INST_MODE, kBig, 512, 1><<<grid, threads, smem_bytes, st>>>(p);
+#endif
+}
+
+}  // namespace bp

@@ -17,7 +17,8 @@
 #include <vector>
 
 #include "../../include/ldpcb200.h"
-#include "bp_kernel.cuh"
+#define BP_WITH_SELFTEST 1
+#include "bp_launch.h"
 #include "bp_math.cuh"
 #include "formats.cuh"
 
@@ -378,70 +379,42 @@ void destroy_device(DeviceCtx &d)
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
-// Instantiations of the persistent kernel.  Shapes: (threads <= 256, 2 CTAs/SM, <= 128 regs),
-// (<= 320, 2, <= 96 regs), (<= 384, 2, <= 80 regs), (<= 512, 1 CTA/SM, <= 128 regs).
-enum KernelShape { kShape256x2 = 0, kShape320x2 = 1, kShape384x2 = 2, kShape512x1 = 3 };
+using bp::kShape256x2;
+using bp::kShape384x2;
+using bp::kShape512x1;
 
 int kernel_shape(bool two_ctas, int threads)
 {
     if (!two_ctas) return kShape512x1;
-    return threads <= 256 ? kShape256x2 : (threads <= 320 ? kShape320x2 : kShape384x2);
+    return threads <= 256 ? kShape256x2 : kShape384x2;
 }
 
-template <int MODE, bool BIG, int MAXT, int MINB>
-int kernel_attrs(int smem_bytes, int threads, int *blocks_per_sm)
-{
-    auto k = bp::bp_persistent_kernel<MODE, BIG, MAXT, MINB>;
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    if (MODE == 0) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes));
-    return 0;
-}
-
-template <int MODE, bool BIG>
-int kernel_attrs_for(int shape, int smem_bytes, int threads, int *bps)
-{
-    switch (shape) {
-        case kShape256x2: return kernel_attrs<MODE, BIG, 256, 2>(smem_bytes, threads, bps);
-        case kShape320x2: return kernel_attrs<MODE, BIG, 320, 2>(smem_bytes, threads, bps);
-        case kShape384x2: return kernel_attrs<MODE, BIG, 384, 2>(smem_bytes, threads, bps);
-        default: return kernel_attrs<MODE, BIG, 512, 1>(smem_bytes, threads, bps);
-    }
-}
-
-template <int MODE, bool BIG>
-void kernel_launch_for(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const bp::KernelParams &p)
-{
-    switch (shape) {
-        case kShape256x2: bp::bp_persistent_kernel<MODE, BIG, 256, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        case kShape320x2: bp::bp_persistent_kernel<MODE, BIG, 320, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        case kShape384x2: bp::bp_persistent_kernel<MODE, BIG, 384, 2><<<grid, threads, smem_bytes, st>>>(p); break;
-        default: bp::bp_persistent_kernel<MODE, BIG, 512, 1><<<grid, threads, smem_bytes, st>>>(p); break;
-    }
-}
-
+// The (MODE, BIG) instantiations live in their own translation units (bp_inst_m*_b*.cu).
 int kernel_attrs_dispatch(int mode, bool big, int shape, int smem_bytes, int threads, int *bps)
 {
+    cudaError_t e;
     switch (mode * 2 + (big ? 1 : 0)) {
-        case 0: return kernel_attrs_for<0, false>(shape, smem_bytes, threads, bps);
-        case 1: return kernel_attrs_for<0, true>(shape, smem_bytes, threads, bps);
-        case 2: return kernel_attrs_for<1, false>(shape, smem_bytes, threads, bps);
-        case 3: return kernel_attrs_for<1, true>(shape, smem_bytes, threads, bps);
-        case 4: return kernel_attrs_for<2, false>(shape, smem_bytes, threads, bps);
-        default: return kernel_attrs_for<2, true>(shape, smem_bytes, threads, bps);
+        case 0: e = bp::kernel_attrs_0_0(shape, smem_bytes, threads, bps); break;
+        case 1: e = bp::kernel_attrs_0_1(shape, smem_bytes, threads, bps); break;
+        case 2: e = bp::kernel_attrs_1_0(shape, smem_bytes, threads, bps); break;
+        case 3: e = bp::kernel_attrs_1_1(shape, smem_bytes, threads, bps); break;
+        case 4: e = bp::kernel_attrs_2_0(shape, smem_bytes, threads, bps); break;
+        default: e = bp::kernel_attrs_2_1(shape, smem_bytes, threads, bps); break;
     }
+    if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "kernel attributes (mode %d): %s", mode, cudaGetErrorString(e));
+    return 0;
 }
 
 void kernel_launch_dispatch(int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
                             const bp::KernelParams &p)
 {
     switch (mode * 2 + (big ? 1 : 0)) {
-        case 0: kernel_launch_for<0, false>(shape, grid, threads, smem_bytes, st, p); break;
-        case 1: kernel_launch_for<0, true>(shape, grid, threads, smem_bytes, st, p); break;
-        case 2: kernel_launch_for<1, false>(shape, grid, threads, smem_bytes, st, p); break;
-        case 3: kernel_launch_for<1, true>(shape, grid, threads, smem_bytes, st, p); break;
-        case 4: kernel_launch_for<2, false>(shape, grid, threads, smem_bytes, st, p); break;
-        default: kernel_launch_for<2, true>(shape, grid, threads, smem_bytes, st, p); break;
+        case 0: bp::kernel_launch_0_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 1: bp::kernel_launch_0_1(shape, grid, threads, smem_bytes, st, p); break;
+        case 2: bp::kernel_launch_1_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 3: bp::kernel_launch_1_1(shape, grid, threads, smem_bytes, st, p); break;
+        case 4: bp::kernel_launch_2_0(shape, grid, threads, smem_bytes, st, p); break;
+        default: bp::kernel_launch_2_1(shape, grid, threads, smem_bytes, st, p); break;
     }
 }
 
@@ -477,7 +450,7 @@ int configure(ldpcb200 *h)
 
     // ---- family SMEM (mode 0): messages of 32 syndromes + state + tables in shared memory
     if (family != LDPCB200_FAMILY_GLOBAL && narrow && h->E > 0) {
-        const int wmax_two = 12, wmax_one = 16;
+        const int wmax_two = h->big ? 8 : 12, wmax_one = 16;   // the local-memory degree path has no 384-thread kernel
         int w = h->opt_warps > 0 ? h->opt_warps : 0;
         // try two CTAs per SM first
         int w2 = w ? std::min(w, wmax_two) : pick_warps(h->s, h->n, 4, wmax_two);
@@ -504,7 +477,8 @@ int configure(ldpcb200 *h)
         // widest CTA (12, 10, 8 warps; two CTAs per SM) whose ring still reaches the full depth,
         // else the one with the deepest ring.  mode 1 (state + tables in shared memory) if it fits.
         std::vector<int> cand;
-        if (h->opt_warps > 0) cand.push_back(std::min(h->opt_warps, 16));
+        if (h->opt_warps > 0) cand.push_back(std::min(h->opt_warps, h->big ? 8 : 12));
+        else if (h->big) cand = {8};
         else cand = {12, 10, 8};
         int best_pd = -1;
         for (int w : cand) {
