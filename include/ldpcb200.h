@@ -35,6 +35,7 @@ typedef struct ldpcb200 ldpcb200_t;
 #define LDPCB200_ENOMEM        5
 
 #define LDPCB200_MAX_DEGREE  128   /* largest check / variable degree the kernels accept */
+#define LDPCB200_MAX_EDGES   8388607 /* nnz(H) limit: edge slot * 256 B must stay below 2^31 */
 
 /* element formats of host matrices at the boundary (column = one syndrome / one error vector,
  * exactly the shapes batchdecode! takes: belief_propagation.jl:220, test_bp_decoder.jl:24-26) */

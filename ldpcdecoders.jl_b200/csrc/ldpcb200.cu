@@ -165,7 +165,8 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
     const int64_t s = h->s, n = h->n;
     if (colptr[0] - base != 0) return fail(LDPCB200_EINVAL, "colptr[0] must equal index_base");
     const int64_t E = colptr[n] - base;
-    if (E < 0 || E > 0x7fffffff / 64) return fail(LDPCB200_EINVAL, "edge count %lld out of range", (long long)E);
+    // message rows are addressed as slot * 256 in 32-bit arithmetic inside the kernels
+    if (E < 0 || E > LDPCB200_MAX_EDGES) return fail(LDPCB200_EUNSUPPORTED, "edge count %lld exceeds LDPCB200_MAX_EDGES", (long long)E);
     h->E = E;
     h->colptr.assign(n + 1, 0);
     h->rowptr.assign(s + 1, 0);

@@ -65,3 +65,17 @@ def test_bad_arguments_are_reported_not_crashed(pkg):
     rc = lib.ldpcb200_create(1, 1, colptr.ctypes.data, colptr.ctypes.data, 7, 0.1, 5, 0, None, 0, ctypes.byref(h))
     assert rc == pkg._lib.EINVAL
     assert lib.ldpcb200_destroy(None) == 0
+
+
+def test_limits_are_reported(pkg):
+    """Degree / edge-count limits give LDPCB200_EUNSUPPORTED or the no-device error, never a crash
+    (graph validation happens before any CUDA call only when a device exists, so on CPU the
+    no-device error wins)."""
+    lib = pkg._lib.load()
+    h = ctypes.c_void_p()
+    n = 200
+    colptr = np.arange(n + 1, dtype=np.int64) * 1      # degree-1 columns, all in check 0 -> check degree 200 > 128
+    rowval = np.zeros(n, dtype=np.int64)
+    rc = lib.ldpcb200_create(1, n, colptr.ctypes.data, rowval.ctypes.data, 0, 0.1, 5, 0, None, 0, ctypes.byref(h))
+    assert rc in (pkg._lib.EUNSUPPORTED, pkg._lib.ENODEVICE)
+    assert lib.ldpcb200_last_error()
