@@ -47,6 +47,9 @@ typedef struct ldpcb200 ldpcb200_t;
 
 /* kernel variants */
 #define LDPCB200_VARIANT_EXACT  0 /* FP64 likelihood-ratio sum-product, op-for-op with belief_propagation.jl:135-178 */
+#define LDPCB200_VARIANT_MINSUM 1 /* min-sum on FP64 log-likelihood ratios; NO reference equivalent (the package's BP is
+                                     sum-product): a faster, non-bit-compatible option.  Same schedule, early stop and
+                                     outputs; posterior_ratio then carries the posterior LLR log(P0/P1). */
 
 /* kernel families (ldpcb200_info_t.family, option "family") */
 #define LDPCB200_FAMILY_AUTO   0
@@ -95,6 +98,7 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
 /* Tunables, set before the first decode (all optional):
  *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA), "prefetch" (cp.async prefetch distance of the
  *   HBM modes, 0..3),
+ *   "minsum_scale_permille" (min-sum variant: normalisation factor x 1000, default 875),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libldpcb200.so")
 OK, EINVAL, ECUDA, ENODEVICE, EUNSUPPORTED, ENOMEM = range(6)
 FMT_U8, FMT_I64, FMT_BITS, FMT_PACKED32, FMT_F64 = range(5)
 FAMILY_AUTO, FAMILY_SMEM, FAMILY_GLOBAL = range(3)
-VARIANT_EXACT = 0
+VARIANT_EXACT, VARIANT_MINSUM = 0, 1
 NUM_COUNTERS = 4
 CTR_DECODED, CTR_CONVERGED, CTR_ITERATIONS = 0, 1, 2
 

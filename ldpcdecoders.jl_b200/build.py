@@ -12,7 +12,8 @@ SRC_DIR = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libldpcb200.so")
-SOURCES = ["ldpcb200.cu"] + ["bp_inst_m%d_b%d.cu" % (m, b) for m in (0, 1, 2) for b in (0, 1)]
+SOURCES = (["ldpcb200.cu"] + ["bp_inst_m%d_b%d.cu" % (m, b) for m in (0, 1, 2) for b in (0, 1)]
+           + ["bp_inst_m%d_b0_minsum.cu" % m for m in (0, 1, 2)])
 HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "bp_launch.h", "bp_launch_inst.cuh", "formats.cuh", "../../include/ldpcb200.h"]
 
 NVCC_FLAGS = [

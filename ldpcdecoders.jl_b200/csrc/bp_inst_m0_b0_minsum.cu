@@ -1,4 +1,4 @@
-#define BP_INST_MODE 2
+#define BP_INST_MODE 0
 #define BP_INST_BIG 0
-#define BP_VARIANT 0
+#define BP_VARIANT 1
 #include "bp_launch_inst.cuh"

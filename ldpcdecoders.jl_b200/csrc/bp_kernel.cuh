@@ -56,7 +56,8 @@ struct KernelParams {
     int SW, NW;               // uint32 words per packed syndrome / error row
     int max_iters;
     int early_stop;           // 1 = reference semantics
-    double p0;                // per / (1 - per)
+    double p0;                // exact: per / (1 - per); min-sum: log((1 - per) / per)
+    double check_aux;         // min-sum: normalisation factor applied to the check->variable magnitude
     int regular_p0;           // p0 is a positive normal double (no NaN clamp can fire on finite messages)
     long long B;
     const uint32_t *syn_words;    // [B][SW]
@@ -210,10 +211,12 @@ __device__ __forceinline__ void load_offsets(uint32_t (&v)[D], TH a)
     }
 }
 
+inline namespace BP_VNS {
+
 // One check node of degree D whose D message slots start at `a` (this lane's column,
 // consecutive slots 256 B apart).
 template <int D, class MH>
-__device__ __forceinline__ void check_node(MH a, bool neg, bool fresh, double p0)
+__device__ __forceinline__ void check_node(MH a, bool neg, bool fresh, double p0, double aux)
 {
     double m[D];
     load_row<D>(m, a);
@@ -221,7 +224,7 @@ __device__ __forceinline__ void check_node(MH a, bool neg, bool fresh, double p0
 #pragma unroll
         for (int k = 0; k < D; ++k) m[k] = p0;
     }
-    check_update<D>(m, neg);
+    check_update<D>(m, neg, aux);
     store_row<D>(m, a);
 }
 
@@ -244,7 +247,7 @@ __device__ __forceinline__ double var_node(MH ml, TH vea, double p0, bool regula
 // Staged forms (modes 1/2): the node's rows were prefetched into a shared-memory ring slot
 // (`ra`, this lane's column); results go straight back to global memory.
 template <int D>
-__device__ __forceinline__ void check_node_staged(uint32_t ra, unsigned char *ga, bool neg, bool fresh, double p0)
+__device__ __forceinline__ void check_node_staged(uint32_t ra, unsigned char *ga, bool neg, bool fresh, double p0, double aux)
 {
     double m[D];
     load_row<D>(m, ra);
@@ -252,7 +255,7 @@ __device__ __forceinline__ void check_node_staged(uint32_t ra, unsigned char *ga
 #pragma unroll
         for (int k = 0; k < D; ++k) m[k] = p0;
     }
-    check_update<D>(m, neg);
+    check_update<D>(m, neg, aux);
     store_row<D>(m, ga);
 }
 template <int D, class TH>
@@ -452,6 +455,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     __syncthreads();
 
     const double p0 = p.p0;
+    const double caux = p.check_aux;                  // min-sum: normalisation factor; exact variant: unused
     const bool regular_p0 = p.regular_p0;
     while (__ballot_sync(0xffffffffu, active) != 0u) {
         // ------------------------------------------------------------------ check pass (:135-150)
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             issue();                                                                             \
             cp_async_wait_pending(p.pd);                                                         \
             __syncwarp();                                                                        \
-            if (active) check_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, ga, syn_bit(i), fresh, p0); \
+            if (active) check_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, ga, syn_bit(i), fresh, p0, caux); \
             __syncwarp();                                                                        \
             cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                        \
         }                                                                                        \
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                         const bool neg = syn_bit(i);
                         const uint32_t ra = ring_w + cslot * p.ring_slot_bytes + lane * 8;
                         unsigned char *ga = msg_generic + static_cast<size_t>(rp) * 256;
-#define BP_CASE(D) check_node_staged<D>(ra, ga, neg, fresh, p0)
+#define BP_CASE(D) check_node_staged<D>(ra, ga, neg, fresh, p0, caux)
                         BP_DEGREE_SWITCH(
                             deg, BP_CASE, if (BIG) {
                                 double *base = reinterpret_cast<double *>(ga);
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         MH a = ml + warp * (D * 256);                                                            \
-        for (int i = warp; i < p.s; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0); \
+        for (int i = warp; i < p.s; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0, caux); \
     }
                 BP_DEGREE_SWITCH(p.uni_cdeg, BP_CASE, ;)
 #undef BP_CASE
@@ -578,9 +582,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     {                                                                                            \
         MH a = ml + (sb + (i - first) * D) * 256;                                                \
         if (p.perm_c)                                                                            \
-            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit(i), fresh, p0); \
+            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit(i), fresh, p0, caux); \
         else                                                                                     \
-            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0); \
+            for (; i < end; i += W, a += W * (D * 256)) check_node<D>(a, syn_bit_direct(i), fresh, p0, caux); \
     }
                     BP_DEGREE_SWITCH(
                         deg, BP_CASE, if (BIG) {
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                     const int deg = rowptr_at(i + 1) - rp;
                     const bool neg = syn_bit(i);
                     const MH a = ml + rp * 256;
-#define BP_CASE(D) check_node<D>(a, neg, fresh, p0)
+#define BP_CASE(D) check_node<D>(a, neg, fresh, p0, caux)
                     BP_DEGREE_SWITCH(
                         deg, BP_CASE, if (BIG) {
                             double *base = reinterpret_cast<double *>(msg_generic + static_cast<size_t>(rp) * 256);
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             // posterior ratio R of this lane's i-th variable j: optional output, hard decision (:163-168)
             auto record = [&](int j, int i, double R) {
                 if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
-                const uint32_t bit = (R >= 1.0) ? 1u : 0u;                            // tie -> 1
+                const uint32_t bit = decide(R) ? 1u : 0u;                            // tie -> 1
                 if (use_regs) {
                     newbits |= static_cast<unsigned long long>(bit) << i;
                 } else {
@@ -781,13 +785,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
                 if (p.ratio) { p.ratio[sid * p.n + j] = Ra; p.ratio[sid * p.n + j + W] = Rb; }   \
-                newbits |= static_cast<unsigned long long>(((Ra >= 1.0) ? 1u : 0u) | ((Rb >= 1.0) ? 2u : 0u)) << i; \
+                newbits |= static_cast<unsigned long long>((decide(Ra) ? 1u : 0u) | (decide(Rb) ? 2u : 0u)) << i; \
             }                                                                                    \
         }                                                                                        \
         for (; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
             if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
-            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
+            newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;               \
         }                                                                                        \
     }
                     BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                         if (deg == 0) {                                               // isolated variables: prior only
                             for (; j < end; j += W, ++i) {
                                 if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = p0;
-                                newbits |= static_cast<unsigned long long>((p0 >= 1.0) ? 1u : 0u) << i;
+                                newbits |= static_cast<unsigned long long>(decide(p0) ? 1u : 0u) << i;
                             }
                             continue;
                         }
@@ -823,13 +827,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                     p.ratio[sid * p.n + vorig_at(j)] = Ra;                                       \
                     p.ratio[sid * p.n + vorig_at(j + W)] = Rb;                                   \
                 }                                                                                \
-                newbits |= static_cast<unsigned long long>(((Ra >= 1.0) ? 1u : 0u) | ((Rb >= 1.0) ? 2u : 0u)) << i; \
+                newbits |= static_cast<unsigned long long>((decide(Ra) ? 1u : 0u) | (decide(Rb) ? 2u : 0u)) << i; \
             }                                                                                    \
         }                                                                                        \
         for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
             if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;                                   \
-            newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;               \
+            newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;               \
         }                                                                                        \
     }
                         BP_DEGREE_SWITCH(
@@ -845,7 +849,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                                         },
                                         deg, p0);
                                     if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
-                                    newbits |= static_cast<unsigned long long>((R >= 1.0) ? 1u : 0u) << i;
+                                    newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;
                                 }
                             })
 #undef BP_CASE
@@ -947,5 +951,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
         }
     }
 }
+
+}  // inline namespace BP_VNS
 
 }  // namespace bp

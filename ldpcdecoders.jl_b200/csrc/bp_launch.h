@@ -11,14 +11,13 @@ namespace bp {
 // the local-memory degree path), (<= 512, 1 CTA/SM, <= 128 regs; mode 0 only).
 enum KernelShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
 
-// Sets the dynamic shared-memory limit and reports resident CTAs per SM.
-cudaError_t kernel_attrs(int mode, bool big, int shape, int smem_bytes, int threads, int *blocks_per_sm);
-void kernel_launch(int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
 
-#define BP_DECLARE_MODE(M, B)                                                                               \
-    cudaError_t kernel_attrs_##M##_##B(int shape, int smem_bytes, int threads, int *blocks_per_sm);       \
-    void kernel_launch_##M##_##B(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
-BP_DECLARE_MODE(0, 0) BP_DECLARE_MODE(0, 1) BP_DECLARE_MODE(1, 0) BP_DECLARE_MODE(1, 1) BP_DECLARE_MODE(2, 0) BP_DECLARE_MODE(2, 1)
+// one pair per translation unit: memory mode M, degree path B (1 = local-memory degrees), variant V
+#define BP_DECLARE_MODE(M, B, V)                                                                            \
+    cudaError_t kernel_attrs_##M##_##B##_##V(int shape, int smem_bytes, int threads, int *blocks_per_sm); \
+    void kernel_launch_##M##_##B##_##V(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
+BP_DECLARE_MODE(0, 0, 0) BP_DECLARE_MODE(0, 1, 0) BP_DECLARE_MODE(1, 0, 0) BP_DECLARE_MODE(1, 1, 0) BP_DECLARE_MODE(2, 0, 0) BP_DECLARE_MODE(2, 1, 0)
+BP_DECLARE_MODE(0, 0, 1) BP_DECLARE_MODE(1, 0, 1) BP_DECLARE_MODE(2, 0, 1)
 #undef BP_DECLARE_MODE
 
 }  // namespace bp

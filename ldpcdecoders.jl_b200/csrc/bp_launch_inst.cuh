@@ -1,8 +1,9 @@
-// bp_launch_inst.cuh -- body of one (BP_INST_MODE, BP_INST_BIG) translation unit.
+// bp_launch_inst.cuh -- body of one (BP_INST_MODE, BP_INST_BIG, BP_VARIANT) translation unit.
 #include "bp_launch.h"
 
-#define BP_CAT3(a, b, c) a##b##_##c
-#define BP_NAME(prefix, m, b) BP_CAT3(prefix, m, b)
+#define BP_CAT4(a, b, c, d) a##b##_##c##_##d
+#define BP_NAME4(prefix, m, b, v) BP_CAT4(prefix, m, b, v)
+#define BP_NAME(prefix, m, b) BP_NAME4(prefix, m, b, BP_VARIANT)
 
 namespace bp {
 

@@ -112,6 +112,7 @@ struct ldpcb200 {
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
+    double ms_scale = 0.875;     // min-sum normalisation factor (option "minsum_scale_permille")
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     // resolved configuration
     bool configured = false;
@@ -390,32 +391,48 @@ int kernel_shape(bool two_ctas, int threads)
     return threads <= 256 ? kShape256x2 : kShape384x2;
 }
 
-// The (MODE, BIG) instantiations live in their own translation units (bp_inst_m*_b*.cu).
-int kernel_attrs_dispatch(int mode, bool big, int shape, int smem_bytes, int threads, int *bps)
+// The (MODE, BIG, VARIANT) instantiations live in their own translation units (bp_inst_*.cu).
+int kernel_attrs_dispatch(int variant, int mode, bool big, int shape, int smem_bytes, int threads, int *bps)
 {
     cudaError_t e;
-    switch (mode * 2 + (big ? 1 : 0)) {
-        case 0: e = bp::kernel_attrs_0_0(shape, smem_bytes, threads, bps); break;
-        case 1: e = bp::kernel_attrs_0_1(shape, smem_bytes, threads, bps); break;
-        case 2: e = bp::kernel_attrs_1_0(shape, smem_bytes, threads, bps); break;
-        case 3: e = bp::kernel_attrs_1_1(shape, smem_bytes, threads, bps); break;
-        case 4: e = bp::kernel_attrs_2_0(shape, smem_bytes, threads, bps); break;
-        default: e = bp::kernel_attrs_2_1(shape, smem_bytes, threads, bps); break;
+    if (variant == LDPCB200_VARIANT_MINSUM) {
+        switch (mode) {
+            case 0: e = bp::kernel_attrs_0_0_1(shape, smem_bytes, threads, bps); break;
+            case 1: e = bp::kernel_attrs_1_0_1(shape, smem_bytes, threads, bps); break;
+            default: e = bp::kernel_attrs_2_0_1(shape, smem_bytes, threads, bps); break;
+        }
+    } else {
+        switch (mode * 2 + (big ? 1 : 0)) {
+            case 0: e = bp::kernel_attrs_0_0_0(shape, smem_bytes, threads, bps); break;
+            case 1: e = bp::kernel_attrs_0_1_0(shape, smem_bytes, threads, bps); break;
+            case 2: e = bp::kernel_attrs_1_0_0(shape, smem_bytes, threads, bps); break;
+            case 3: e = bp::kernel_attrs_1_1_0(shape, smem_bytes, threads, bps); break;
+            case 4: e = bp::kernel_attrs_2_0_0(shape, smem_bytes, threads, bps); break;
+            default: e = bp::kernel_attrs_2_1_0(shape, smem_bytes, threads, bps); break;
+        }
     }
     if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "kernel attributes (mode %d): %s", mode, cudaGetErrorString(e));
     return 0;
 }
 
-void kernel_launch_dispatch(int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
+void kernel_launch_dispatch(int variant, int mode, bool big, int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
                             const bp::KernelParams &p)
 {
+    if (variant == LDPCB200_VARIANT_MINSUM) {
+        switch (mode) {
+            case 0: bp::kernel_launch_0_0_1(shape, grid, threads, smem_bytes, st, p); break;
+            case 1: bp::kernel_launch_1_0_1(shape, grid, threads, smem_bytes, st, p); break;
+            default: bp::kernel_launch_2_0_1(shape, grid, threads, smem_bytes, st, p); break;
+        }
+        return;
+    }
     switch (mode * 2 + (big ? 1 : 0)) {
-        case 0: bp::kernel_launch_0_0(shape, grid, threads, smem_bytes, st, p); break;
-        case 1: bp::kernel_launch_0_1(shape, grid, threads, smem_bytes, st, p); break;
-        case 2: bp::kernel_launch_1_0(shape, grid, threads, smem_bytes, st, p); break;
-        case 3: bp::kernel_launch_1_1(shape, grid, threads, smem_bytes, st, p); break;
-        case 4: bp::kernel_launch_2_0(shape, grid, threads, smem_bytes, st, p); break;
-        default: bp::kernel_launch_2_1(shape, grid, threads, smem_bytes, st, p); break;
+        case 0: bp::kernel_launch_0_0_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 1: bp::kernel_launch_0_1_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 2: bp::kernel_launch_1_0_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 3: bp::kernel_launch_1_1_0(shape, grid, threads, smem_bytes, st, p); break;
+        case 4: bp::kernel_launch_2_0_0(shape, grid, threads, smem_bytes, st, p); break;
+        default: bp::kernel_launch_2_1_0(shape, grid, threads, smem_bytes, st, p); break;
     }
 }
 
@@ -515,7 +532,7 @@ int configure(ldpcb200 *h)
     int bps = 0, rc;
     for (DeviceCtx &d : h->dev) {
         CU(cudaSetDevice(d.device));
-        rc = kernel_attrs_dispatch(mode, h->big, shape, need, warps * 32, &bps);
+        rc = kernel_attrs_dispatch(h->variant, mode, h->big, shape, need, warps * 32, &bps);
         if (rc) return rc;
     }
     if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "BP kernel (mode %d, %d threads, %d B smem) does not fit on an SM", mode, warps * 32, need);
@@ -557,6 +574,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     p.SW = h->SW; p.NW = h->NW; p.uni_cdeg = h->uni_cdeg; p.uni_vdeg = h->uni_vdeg;
     p.max_iters = h->max_iters; p.early_stop = h->opt_early_stop; p.p0 = h->p0; p.B = B;
     p.regular_p0 = h->regular_p0;
+    p.check_aux = h->ms_scale;
     p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
     p.counters = counters;
     p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
@@ -581,7 +599,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     }
     // finished lanes OR their set decision bits into the row: rows start out zero
     CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
-    kernel_launch_dispatch(h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
+    kernel_launch_dispatch(h->variant, h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -757,7 +775,10 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
         return fail(LDPCB200_EINVAL, "bad shape / null colptr / index_base not 0 or 1");
     if (s > 0x3fffffff || n > 0x3fffffff) return fail(LDPCB200_EINVAL, "matrix too large");
     if (!rowval && colptr[n] - index_base != 0) return fail(LDPCB200_EINVAL, "rowval is null");
-    if (variant != LDPCB200_VARIANT_EXACT) return fail(LDPCB200_EUNSUPPORTED, "variant %d not available", variant);
+    if (variant != LDPCB200_VARIANT_EXACT && variant != LDPCB200_VARIANT_MINSUM)
+        return fail(LDPCB200_EUNSUPPORTED, "variant %d not available", variant);
+    if (variant == LDPCB200_VARIANT_MINSUM && !(per > 0.0 && per < 1.0))
+        return fail(LDPCB200_EINVAL, "the min-sum variant needs 0 < per < 1 (finite prior log-likelihood ratio)");
     if (max_iters < 0) max_iters = 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -772,9 +793,17 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
         volatile double q = per / one_minus;
         h->p0 = q;
         h->regular_p0 = std::isnormal(h->p0) && h->p0 > 0.0;
+        if (variant == LDPCB200_VARIANT_MINSUM) {      // the kernels' prior slot carries L0 = log((1-p)/p)
+            volatile double r = one_minus / per;
+            h->p0 = std::log(r);
+        }
     }
     int rc = build_graph(h, colptr, rowval, index_base);
     if (rc) { delete h; return rc; }
+    if (variant == LDPCB200_VARIANT_MINSUM && h->big) {
+        delete h;
+        return fail(LDPCB200_EUNSUPPORTED, "the min-sum variant supports node degrees up to %d", bp::kMaxRegDegree);
+    }
     std::vector<int> devs;
     if (devices && ndev > 0) devs.assign(devices, devices + ndev); else devs.push_back(0);
     for (int dv : devs) {
@@ -804,6 +833,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     const std::string k(key);
     if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration
     if (k == "chunk") { h->opt_chunk = value; return 0; }
+    if (k == "minsum_scale_permille") { h->ms_scale = static_cast<double>(value) / 1000.0; return 0; }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);

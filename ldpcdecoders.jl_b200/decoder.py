@@ -42,9 +42,10 @@ def _fmt_of(a, what):
 
 class BeliefPropagationDecoder:
     """BeliefPropagationDecoder(H, per, max_iters) -- fields per, max_iters, s, n, sparse_H,
-    sparse_HT, scratch as in belief_propagation.jl:38-59; the Tanner graph lives on the GPU."""
+    sparse_HT, scratch as in belief_propagation.jl:38-59; the Tanner graph lives on the GPU.
+    variant="minsum" selects the (non-reference) min-sum kernels; default is the exact replica."""
 
-    def __init__(self, H, per, max_iters, devices=None, **options):
+    def __init__(self, H, per, max_iters, devices=None, variant="exact", **options):
         if not isinstance(per, float):
             raise TypeError("per must be a Float64 (belief_propagation.jl:61)")
         if isinstance(max_iters, bool) or not isinstance(max_iters, (int, np.integer)):
@@ -57,6 +58,7 @@ class BeliefPropagationDecoder:
         self.s, self.n = (int(x) for x in Hc.shape)
         self.sparse_H = Hc
         self.sparse_HT = Hc.T.tocsc()
+        self.variant = variant
         self.scratch = BeliefPropagationScratchSpace(self.n)
         lib = _lib.load()
         colptr = np.ascontiguousarray(Hc.indptr, dtype=np.int64)
@@ -68,7 +70,8 @@ class BeliefPropagationDecoder:
             ndev = len(devs)
         h = ctypes.c_void_p()
         _lib.check(lib.ldpcb200_create(self.s, self.n, colptr.ctypes.data, rowval.ctypes.data, 0,
-                                       self.per, self.max_iters, _lib.VARIANT_EXACT,
+                                       self.per, self.max_iters,
+                                       {"exact": _lib.VARIANT_EXACT, "minsum": _lib.VARIANT_MINSUM}[variant],
                                        devs.ctypes.data if devs is not None else None, ndev,
                                        ctypes.byref(h)))
         self._h = h
@@ -192,7 +195,9 @@ def decode_b(decoder, syndrome):
         ratio = np.ones((decoder.n, 1), dtype=np.float64, order="F")
     decoder.last_counters = decoder.decode_raw(1, syn_f, _fmt_of(syn_f, "syndrome"), max(decoder.s, 1), err,
                                                _lib.FMT_F64, max(decoder.n, 1), conv, None, ratio)
-    if ratio is not None:
+    if ratio is not None and decoder.variant == "minsum":
+        decoder.scratch.log_probabs[:] = ratio[:, 0]                      # posterior LLR log(P0/P1)
+    elif ratio is not None:
         with np.errstate(all="ignore"):
             decoder.scratch.log_probabs[:] = np.log(1.0 / ratio[:, 0])   # belief_propagation.jl:163
     else:

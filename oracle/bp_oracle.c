@@ -143,6 +143,75 @@ static int decode_edge(const graph_t *g, double per, int max_iters, const uint8_
     return converged;
 }
 
+/* Min-sum variant (LDPCB200_VARIANT_MINSUM).  NOT a restatement of the reference -- the package's
+ * BeliefPropagationDecoder is sum-product only -- but the definition the CUDA min-sum kernels are
+ * checked against: flooding schedule, early stop, tie rule and outputs as in decode_edge(),
+ * messages are log-likelihood ratios L = log(P0/P1), prior L0 = log((1-per)/per).
+ *   check i : out_k = (-1)^{s_i} * prod_{j!=k} sgn(L_j) * (alpha * min_{j!=k} |L_j|)   (first minimum wins ties;
+ *             alpha = normalisation factor, default 0.875, bp_oracle_set_minsum_scale)
+ *   var j   : T_0 = L0, T_{k+1} = T_k + M_k; U_last = 0, U_{k-1} = U_k + M_k; out_k = T_k + U_k
+ *   decision: 1 iff posterior T_D <= 0.   ratio[] receives the posterior LLR. */
+static double g_minsum_scale = 0.875;
+void bp_oracle_set_minsum_scale(double a) { g_minsum_scale = a; }
+
+static int decode_edge_minsum(const graph_t *g, double per, int max_iters, const uint8_t *syn,
+                              double *b2c, double *c2b, uint8_t *err, double *ratio, int32_t *iters_out)
+{
+    const int64_t s = g->s, n = g->n;
+    volatile double one_minus = 1.0 - per;
+    volatile double r = one_minus / per;
+    const double L0 = log(r);
+    memset(err, 0, (size_t)n);
+    if (ratio) for (int64_t j = 0; j < n; ++j) ratio[j] = 0.0;
+    for (int64_t e = 0; e < g->E; ++e) b2c[e] = L0;
+    int converged = 0;
+    int32_t it = 0;
+    for (int iter = 1; iter <= max_iters; ++iter) {
+        it = iter;
+        for (int64_t i = 0; i < s; ++i) {
+            int par = syn[i] ? 1 : 0;
+            double m1 = INFINITY, m2 = INFINITY;
+            int64_t idx = -1;
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) {
+                const double L = b2c[g->rowedge[k]];
+                par ^= signbit(L) ? 1 : 0;
+                const double a = fabs(L);
+                if (a < m1) { m2 = m1; m1 = a; idx = k; }
+                else if (a < m2) m2 = a;
+            }
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) {
+                const int64_t e = g->rowedge[k];
+                const double mag = ((k == idx) ? m2 : m1) * g_minsum_scale;
+                const int sk = par ^ (signbit(b2c[e]) ? 1 : 0);
+                c2b[e] = sk ? -mag : mag;
+            }
+        }
+        for (int64_t j = 0; j < n; ++j) {
+            double run = L0;
+            for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e) {
+                b2c[e] = run;
+                run = run + c2b[e];
+            }
+            if (ratio) ratio[j] = run;
+            err[j] = (run <= 0) ? 1 : 0;
+            double U = 0.0;
+            for (int64_t e = g->colptr[j + 1] - 1; e >= g->colptr[j]; --e) {
+                b2c[e] = b2c[e] + U;
+                U = U + c2b[e];
+            }
+        }
+        int ok = 1;
+        for (int64_t i = 0; i < s && ok; ++i) {
+            unsigned par = 0;
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) par ^= err[g->rowvar[k]];
+            if (par != (unsigned)syn[i]) ok = 0;
+        }
+        if (ok) { converged = 1; break; }
+    }
+    if (iters_out) *iters_out = (max_iters > 0) ? it : 0;
+    return converged;
+}
+
 /* One decode!, dense "faithful cost" storage: two s*n column-major matrices exactly like
  * BeliefPropagationScratchSpace (belief_propagation.jl:3-22), full reset per call (:83-91),
  * and the allocating mat-vec of :180-181. */
@@ -231,6 +300,7 @@ int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
                     const uint8_t *syn, uint8_t *err, uint8_t *conv,
                     int32_t *iters, double *ratio, int32_t nthreads, int32_t dense)
 {
+    /* dense: 0 = edge-indexed, 1 = dense faithful cost, 2 = min-sum variant (edge-indexed) */
     graph_t g;
     int rc = build_graph(&g, s, n, colptr, rowval);
     if (rc) return rc;
@@ -241,7 +311,7 @@ int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
 #endif
     {
         double *a = NULL, *b = NULL, *errd = NULL, *chan = NULL, *logp = NULL;
-        size_t msz = dense ? (size_t)s * (size_t)n : (size_t)g.E;
+        size_t msz = (dense == 1) ? (size_t)s * (size_t)n : (size_t)g.E;
         if (msz == 0) msz = 1;
         a = (double *)malloc(sizeof(double) * msz);
         b = (double *)malloc(sizeof(double) * msz);
@@ -262,8 +332,9 @@ int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
                 uint8_t *ec = err + (size_t)c * (size_t)n;
                 double *rc_ = ratio ? ratio + (size_t)c * (size_t)n : NULL;
                 int32_t itc = 0;
-                int cv = dense ? decode_dense(&g, per, max_iters, sc, a, b, errd, chan, logp, ec, rc_, &itc)
-                               : decode_edge(&g, per, max_iters, sc, a, b, ec, rc_, &itc);
+                int cv = (dense == 1) ? decode_dense(&g, per, max_iters, sc, a, b, errd, chan, logp, ec, rc_, &itc)
+                       : (dense == 2) ? decode_edge_minsum(&g, per, max_iters, sc, a, b, ec, rc_, &itc)
+                                      : decode_edge(&g, per, max_iters, sc, a, b, ec, rc_, &itc);
                 conv[c] = (uint8_t)cv;
                 if (iters) iters[c] = itc;
             }

@@ -45,6 +45,8 @@ def load():
     lib.bp_oracle_sample.restype = ctypes.c_int
     lib.bp_oracle_sample.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double,
                                      ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, u8p, u8p]
+    lib.bp_oracle_set_minsum_scale.argtypes = [ctypes.c_double]
+    lib.bp_oracle_set_minsum_scale.restype = None
     lib.bp_oracle_threshold.restype = ctypes.c_uint32
     lib.bp_oracle_threshold.argtypes = [ctypes.c_double]
     lib.bp_oracle_num_threads.restype = ctypes.c_int
@@ -67,10 +69,13 @@ def _p(a, ct):
     return a.ctypes.data_as(ctypes.POINTER(ct))
 
 
-def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_ratio=False):
-    """Restated batchdecode!.  syndromes: (s, B) array of 0/1 (column = syndrome).
+def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_ratio=False, variant="exact",
+                 minsum_scale=0.875):
+    """Restated batchdecode! (variant="minsum": the min-sum definition the CUDA min-sum kernels are
+    checked against -- no reference equivalent).  syndromes: (s, B) array of 0/1 (column = syndrome).
     Returns dict(errors (n,B) uint8, converged (B,) bool, iters (B,) int32[, ratio (n,B) f64])."""
     lib = load()
+    lib.bp_oracle_set_minsum_scale(float(minsum_scale))
     s, n, colptr, rowval = csc_arrays(H)
     syn = np.asfortranarray(np.asarray(syndromes).astype(np.uint8))
     if syn.ndim == 1:
@@ -86,7 +91,7 @@ def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_rat
                              _p(err, ctypes.c_uint8), _p(conv, ctypes.c_uint8),
                              _p(iters, ctypes.c_int32),
                              _p(ratio, ctypes.c_double) if want_ratio else None,
-                             int(nthreads), 1 if dense else 0)
+                             int(nthreads), 2 if variant == "minsum" else (1 if dense else 0))
     if rc != 0:
         raise RuntimeError("bp_oracle_batch failed: %d" % rc)
     out = dict(errors=err, converged=conv.astype(bool), iters=iters)

@@ -369,3 +369,53 @@ def test_in_library_sharding_over_two_devices(pkg, oracle, codes):
     g = dict(errors=errors, converged=success, iters=iters, counters=dec.last_counters)
     dec.close()
     assert_same(g, ref)
+
+
+def run_gpu_variant(pkg, H, per, max_iters, syn, variant, **opts):
+    dec = pkg.BeliefPropagationDecoder(H, per, max_iters, variant=variant, **opts)
+    n, B = H.shape[1], syn.shape[1]
+    errors = np.zeros((n, B), dtype=np.uint8, order="F")
+    iters = np.zeros(B, dtype=np.int32)
+    llr = np.zeros((n, B), dtype=np.float64, order="F")
+    _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn), errors, iters=iters, posterior_ratio=llr)
+    out = dict(errors=errors, converged=success, iters=iters, ratio=llr, info=dec.info(), counters=dec.last_counters.copy())
+    dec.close()
+    return out
+
+
+@pytest.mark.parametrize("name,per,B", [("C3", 0.03, 3000), ("C3", 0.1, 1000), ("C2", 0.02, 2000), ("C4", 0.03, 400), ("C1", 0.03, 100)])
+def test_minsum_variant_matches_its_definition(pkg, oracle, codes, name, per, B):
+    """LDPCB200_VARIANT_MINSUM has no reference equivalent; the CUDA kernels must reproduce the
+    CPU checker's min-sum definition (oracle/bp_oracle.c: decode_edge_minsum) bit for bit."""
+    H, _, mi = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 4321, 0, B)
+    ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads(), variant="minsum", want_ratio=True)
+    g = run_gpu_variant(pkg, H, per, mi, syn, "minsum")
+    assert_same(g, ref, want_ratio=True)
+
+
+def test_minsum_large_code_and_scale_option(pkg, oracle, codes):
+    H, per, mi = codes.config_matrix("C5")
+    _, syn = oracle.sample(H, per, 99, 0, 24)
+    ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads(), variant="minsum")
+    g = run_gpu_variant(pkg, H, per, mi, syn, "minsum")
+    assert g["info"]["kernel_mode"] == 2
+    assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["iters"], ref["iters"])
+    # plain (unnormalised) min-sum through the scale option
+    H, _, mi = codes.config_matrix("C3")
+    _, syn = oracle.sample(H, 0.03, 98, 0, 500)
+    ref = oracle.batch_decode(H, 0.03, mi, syn, variant="minsum", minsum_scale=1.0)
+    g = run_gpu_variant(pkg, H, 0.03, mi, syn, "minsum", minsum_scale_permille=1000)
+    assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["iters"], ref["iters"])
+
+
+def test_minsum_quality_is_close_to_sum_product(pkg, oracle, codes):
+    """Normalised min-sum (0.875) on the gross code: logical quality within a point of sum-product."""
+    H, _, mi = codes.config_matrix("C3")
+    errs, syn = oracle.sample(H, 0.03, 5, 0, 20000)
+    ms = run_gpu_variant(pkg, H, 0.03, mi, syn, "minsum")
+    sp = run_gpu_variant(pkg, H, 0.03, mi, syn, "exact")
+    ok_ms = (ms["errors"] == errs).all(axis=0).mean()
+    ok_sp = (sp["errors"] == errs).all(axis=0).mean()
+    assert ok_ms > ok_sp - 0.01, (ok_ms, ok_sp)
+    assert ms["converged"].mean() > 0.97

@@ -152,3 +152,20 @@ def test_golden_fixtures(oracle, fixture):
     assert np.array_equal(r["converged"], z["converged"])
     assert np.array_equal(r["iters"], z["iters"])
     assert np.array_equal(r["ratio"].view(np.uint64), z["ratio_bits"])
+
+
+def test_minsum_definition_sanity(oracle, codes):
+    """The min-sum checker (no reference equivalent): single bit-flips on the gross code decode,
+    converged <=> syndrome reproduced, threads == serial."""
+    H, _, mi = codes.config_matrix("C3")
+    n = H.shape[1]
+    E = np.eye(n, dtype=np.uint8)
+    syn = np.asarray((H @ E) % 2)
+    r = oracle.batch_decode(H, 0.01, mi, syn, variant="minsum")
+    assert r["converged"].all() and np.array_equal(r["errors"], E)
+    _, syn = oracle.sample(H, 0.06, 3, 0, 400)
+    a = oracle.batch_decode(H, 0.06, mi, syn, variant="minsum", want_ratio=True)
+    b = oracle.batch_decode(H, 0.06, mi, syn, variant="minsum", want_ratio=True, nthreads=4)
+    assert np.array_equal(a["errors"], b["errors"]) and np.array_equal(a["ratio"], b["ratio"], equal_nan=True)
+    ok = (np.asarray((H @ a["errors"]) % 2) == syn).all(axis=0)
+    assert np.array_equal(ok, a["converged"])
