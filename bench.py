@@ -178,7 +178,7 @@ def config_dict(args, H, per, mi, B):
         args.workload, {"C1": "Gallager (1000,10,9)", "C2": "d=15 rotated surface X checks",
                         "C3": "[[144,12,12]] gross code H_X", "C4": "HGP of Gallager(32,4,3) H_X",
                         "C5": "Gallager (100002,6,3)"}[args.workload], s, n, H.nnz, per, mi, B),
-            "per": per, "max_iters": mi, "batch_per_gpu": B,
+            "per": per, "max_iters": mi, "batch_per_gpu": B, "variant": getattr(args, "variant", "exact"),
             "l2": "inputs+outputs of one step exceed the 126 MB L2" if B * ((s + 31) // 32 + (n + 31) // 32) * 4 > 130e6
             else "L2 flushed between steps (256 MB write)"}
 
@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--family", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1)
+    ap.add_argument("--variant", default="exact", choices=["exact", "minsum"],
+                    help="exact = reference-parity sum-product (headline); minsum = normalised min-sum (no reference equivalent)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -247,7 +249,7 @@ def main():
         opts["warps"] = args.warps
     if args.prefetch >= 0:
         opts["prefetch"] = args.prefetch
-    dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], **opts)
+    dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant=args.variant, **opts)
     info = dec.info()
     SW, NW = info["syn_words"], info["err_words"]
     # a non-default torch stream: its handle is non-NULL, so the library launches on exactly the
@@ -428,6 +430,27 @@ def main():
                       "fp64_frac": float(c2[2]) / 2 / world * E * FP64_SLOTS_PER_EDGE_ITER / (secs2 / 2) / 1e12 /
                       (info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12)})
         line["sweep"] = sweep
+
+    # ---- sum-product vs min-sum (BASELINE.json config 3): the normalised min-sum kernels on the same
+    # syndromes; no reference equivalent, so it is reported by quality, not parity
+    if world == 1 and not args.no_sweep and args.variant == "exact" and args.workload in ("C2", "C3"):
+        errw_sp = errw.clone()
+        dms = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant="minsum")
+        dec_saved = dec
+        dec = dms
+        secs2, c2_, _ = timed_run(3, 2)
+        score.zero_()
+        dms.score_device(B, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), score.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        differ = int((errw != errw_sp).any(dim=1).sum().item())
+        line["minsum"] = {"value": float(c2_[0]) / secs2, "unit": UNIT, "per": per, "scale": 0.875,
+                          "mean_iters": float(c2_[2]) / float(c2_[0]), "converged_frac": float(c2_[1]) / float(c2_[0]),
+                          "exact_match_frac": float(score[0].item()) / B,
+                          "decisions_differ_from_sum_product_frac": differ / B,
+                          "note": "FP64 log-likelihood-ratio min-sum, same schedule/early stop; sum-product exact_match_frac is the line's own"}
+        dec = dec_saved
+        dms.close()
+        del errw_sp
 
     # ---- config C2 of BASELINE.json next to the headline (1 M syndromes, per sweep), N = 1 only
     if world == 1 and not args.no_sweep and args.workload == "C3":
