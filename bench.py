@@ -488,6 +488,86 @@ def main():
             del t2, s2, e2, cv2
         line["config_C2_surface_d15_1M"] = c2
 
+    # ---- BASELINE.json config 4 is "the BP stage of BP+OSD": the whole BP -> OSD-0 pipeline on the same syndromes
+    # (ldpcb200_decode_device with posterior ratios, then ldpcb200_osd0_device on the unconverged ones)
+    if world == 1 and not args.no_sweep and args.workload == "C4" and args.variant == "exact":
+        Bo = int(min(B, 131072))
+        ratio = torch.empty((Bo, n), dtype=torch.float64, device=dev)
+        stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        sc_bp = torch.zeros(2, dtype=torch.int64, device=dev)
+        sc_osd = torch.zeros(2, dtype=torch.int64, device=dev)
+
+        def bp_stage():
+            dec.decode_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), ratio.data_ptr(),
+                              ctr.data_ptr(), stream=st)
+
+        def osd_stage():
+            dec.osd0_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), ratio.data_ptr(), stats.data_ptr(), stream=st)
+
+        dec.set_option("ratio_last_only", 1)
+        for _ in range(2):
+            bp_stage()
+            osd_stage()
+        torch.cuda.synchronize()
+        reps = 3
+        t_bp = t_osd = 0.0
+        stats.zero_()
+        ctr.zero_()
+        for _ in range(reps):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            bp_stage()
+            e1.record(stream)
+            if _ == 0:
+                dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_bp.data_ptr(), stream=st)
+                torch.cuda.synchronize()
+            e1b = torch.cuda.Event(enable_timing=True)
+            e1b.record(stream)
+            osd_stage()
+            e2.record(stream)
+            torch.cuda.synchronize()
+            t_bp += e0.elapsed_time(e1) / 1e3
+            t_osd += e1b.elapsed_time(e2) / 1e3
+        dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_osd.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        so = stats.cpu().numpy()
+        nproc = float(so[0]) / reps
+        if os.environ.get("LDPCB200_OSD_PROFILE"):     # one extra pass with the kernel's per-phase cycle counters on
+            dec.set_option("osd_profile", 1)
+            stats.zero_()
+            bp_stage()
+            osd_stage()
+            torch.cuda.synchronize()
+            sp_ = stats.cpu().numpy()
+            sys.stderr.write("osd phases (SM cycles per syndrome): sort %.0f build %.0f search %.0f update %.0f solve %.0f\n" %
+                             tuple(float(sp_[k]) / max(float(sp_[0]), 1.0) for k in (3, 4, 5, 6, 7)))
+            dec.set_option("osd_profile", 0)
+        bposd = {"batch": Bo, "per": per, "value": Bo * reps / (t_bp + t_osd), "unit": UNIT,
+                 "bp_stage_syndromes_per_s": Bo * reps / t_bp,
+                 "osd_stage_syndromes_per_s": float(so[0]) / t_osd if t_osd > 0 else None,
+                 "osd_stage_ms": t_osd / reps * 1e3, "bp_stage_ms": t_bp / reps * 1e3,
+                 "unconverged_frac": nproc / Bo,
+                 "mean_pivots": float(so[1]) / max(float(so[0]), 1.0), "mean_columns_visited": float(so[2]) / max(float(so[0]), 1.0),
+                 "bp_exact_match_frac": float(sc_bp[0].item()) / Bo, "bp_syndrome_satisfied_frac": float(sc_bp[1].item()) / Bo,
+                 "bposd_exact_match_frac": float(sc_osd[0].item()) / Bo,
+                 "bposd_syndrome_satisfied_frac": float(sc_osd[1].item()) / Bo,
+                 "note": "device-resident; the BP stage writes posterior ratios only in iteration max_iters (ratio_last_only)"}
+        if not args.no_cpu:
+            import time as _t
+            oracle = entry.load_oracle()
+            nth = oracle.num_threads()
+            Kc = 8 * nth
+            _, syn_c = oracle.sample(H, per, SEED_E, 0, Kc)
+            oracle.bposd_decode(H, per, mi, syn_c[:, :nth], nthreads=nth)
+            t0 = _t.perf_counter()
+            oracle.bposd_decode(H, per, mi, syn_c, nthreads=nth)
+            dt = _t.perf_counter() - t0
+            bposd["cpu_baseline"] = {"value": Kc / dt, "unit": UNIT, "cores": nth, "kind": "port",
+                                     "sample": "first %d syndromes of the same stream, BP + restated OSD-0 (bit-packed rows)" % Kc}
+        line["bposd_osd0"] = bposd
+        dec.set_option("ratio_last_only", 0)
+        del ratio
+
     # ---- CPU baseline next to it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
         oracle = entry.load_oracle()

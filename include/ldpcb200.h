@@ -79,6 +79,12 @@ typedef struct {
 #define LDPCB200_CTR_RESERVED    3
 #define LDPCB200_NUM_COUNTERS    4
 
+/* OSD-0 statistics (ldpcb200_bposd_decode_batch / ldpcb200_osd0_device) */
+#define LDPCB200_OSD_PROCESSED   0  /* syndromes that went through OSD-0 (= BP did not converge) */
+#define LDPCB200_OSD_PIVOTS      1  /* sum of pivots taken */
+#define LDPCB200_OSD_COLUMNS     2  /* sum of sorted columns visited before the target vanished */
+#define LDPCB200_NUM_OSD_STATS   3
+
 const char *ldpcb200_last_error(void);
 int ldpcb200_version(void);
 int ldpcb200_device_count(int32_t *out);
@@ -100,7 +106,9 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   HBM modes, 0..3),
  *   "minsum_scale_permille" (min-sum variant: normalisation factor x 1000, default 875),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
- *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk). */
+ *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk),
+ *   "ratio_last_only" (ldpcb200_decode_device writes d_posterior_ratio only in iteration max_iters: all an OSD
+ *   stage needs, since it only reads the ratios of syndromes that did not converge; default 0). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);
 
 /* Replaces batchdecode!(decoder, syndromes, errors, success)
@@ -129,6 +137,27 @@ int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
                            const uint32_t *d_syn_words, uint32_t *d_err_words,
                            uint8_t *d_converged, int32_t *d_iters, double *d_posterior_ratio,
                            unsigned long long *d_counters, void *stream);
+
+/* Replaces decode!(::BeliefPropagationOSDDecoder, syndrome) with osd_order = 0
+ * (src/decoders/belief_propagation_osd.jl:49-61, osd(..., Val(0)) :63-125), applied to every column of a
+ * batch: BP as ldpcb200_decode_batch, then OSD-0 on the syndromes BP left unconverged (the reference returns
+ * BP's own decision for the converged ones, :72-74).  errors receives the OSD result, converged BP's flag
+ * (:60 returns BP's `converged`).  osd_stats: nullable, LDPCB200_NUM_OSD_STATS int64.  Exact variant only;
+ * the bit-packed s x (n+1) matrix must fit in shared memory (LDPCB200_EUNSUPPORTED otherwise).
+ * Sort key: max(r, 1-r) with r = RN(1/R_j) where the reference has exp(log(1/R_j)). */
+int ldpcb200_bposd_decode_batch(ldpcb200_t *h, int64_t B,
+                                const void *syndromes, int32_t syn_fmt, int64_t syn_ld,
+                                void *errors, int32_t err_fmt, int64_t err_ld,
+                                uint8_t *converged, int32_t *iters, int64_t *counters, int64_t *osd_stats);
+
+/* The OSD-0 stage alone on device-resident buffers (native packed rows), after ldpcb200_decode_device with a
+ * posterior-ratio output: d_err_words holds BP's decisions on entry and the OSD result on return;
+ * d_posterior_ratio is [B][n].  d_stats: nullable device pointer to LDPCB200_NUM_OSD_STATS uint64 the kernel
+ * ADDS to (8 uint64 when the option "osd_profile" is set: [3..7] then receive SM cycles of the kernel's sort /
+ * build / pivot search / row update / solve phases).  Asynchronous on `stream`. */
+int ldpcb200_osd0_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
+                         const uint32_t *d_syn_words, uint32_t *d_err_words, const uint8_t *d_converged,
+                         const double *d_posterior_ratio, unsigned long long *d_stats, void *stream);
 
 /* Harness helpers (pattern of test/test_bp_decoder.jl:19-30 moved on-device).
  * sample: i.i.d. Bernoulli(per) errors from Philox4x32-10 keyed by the global syndrome index

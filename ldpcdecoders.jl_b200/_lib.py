@@ -14,6 +14,7 @@ FMT_U8, FMT_I64, FMT_BITS, FMT_PACKED32, FMT_F64 = range(5)
 FAMILY_AUTO, FAMILY_SMEM, FAMILY_GLOBAL = range(3)
 VARIANT_EXACT, VARIANT_MINSUM = 0, 1
 NUM_COUNTERS = 4
+NUM_OSD_STATS = 3      # processed, pivots, columns visited
 CTR_DECODED, CTR_CONVERGED, CTR_ITERATIONS = 0, 1, 2
 
 # every exported symbol of include/ldpcb200.h (tests check the .so against this list)
@@ -22,6 +23,7 @@ SYMBOLS = [
     "ldpcb200_destroy", "ldpcb200_info", "ldpcb200_set_option", "ldpcb200_decode_batch",
     "ldpcb200_decode_device", "ldpcb200_sample_device", "ldpcb200_score_device",
     "ldpcb200_launch_count", "ldpcb200_selftest_division",
+    "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device",
 ]
 
 
@@ -65,6 +67,8 @@ def load():
     lib.ldpcb200_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.ldpcb200_decode_batch.argtypes = [vp, i64, vp, i32, i64, vp, i32, i64, vp, vp, vp, vp]
     lib.ldpcb200_decode_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.ldpcb200_bposd_decode_batch.argtypes = [vp, i64, vp, i32, i64, vp, i32, i64, vp, vp, vp, vp]
+    lib.ldpcb200_osd0_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.ldpcb200_sample_device.argtypes = [vp, i32, i64, i64, u64, dbl, vp, vp, vp]
     lib.ldpcb200_score_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
     lib.ldpcb200_launch_count.argtypes = [vp, ctypes.POINTER(i64)]

@@ -10,11 +10,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-OBJ_DIR = os.path.join(LIB_DIR, "obj")
+OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")   # cached objects (git- and gpurun-ignored)
 LIB = os.path.join(LIB_DIR, "libldpcb200.so")
 SOURCES = (["ldpcb200.cu"] + ["bp_inst_m%d_b%d.cu" % (m, b) for m in (0, 1, 2) for b in (0, 1)]
            + ["bp_inst_m%d_b0_minsum.cu" % m for m in (0, 1, 2)])
-HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "bp_launch.h", "bp_launch_inst.cuh", "formats.cuh", "../../include/ldpcb200.h"]
+KERNEL_HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "bp_launch.h", "bp_launch_inst.cuh", "../../include/ldpcb200.h"]
+HEADERS = KERNEL_HEADERS + ["formats.cuh", "osd.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,9 +42,19 @@ def build_library(force=False, verbose=False):
     pid = os.getpid()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, "%s.%d.o" % (src[:-3], pid))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(SRC_DIR, src)]
+        # objects are cached next to the library; a unit is recompiled when it or a header it includes changed
+        obj = os.path.join(OBJ_DIR, "%s.o" % src[:-3])
+        deps = [os.path.join(SRC_DIR, f) for f in [src] + (HEADERS if src == "ldpcb200.cu" else KERNEL_HEADERS)]
+        deps.append(os.path.abspath(__file__))
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+            return src, obj, "(cached) " + obj, 0, ""
+        tmp_obj = obj + ".tmp.%d" % pid
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", tmp_obj, os.path.join(SRC_DIR, src)]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode == 0:
+            os.replace(tmp_obj, obj)
+        elif os.path.exists(tmp_obj):
+            os.remove(tmp_obj)
         return src, obj, " ".join(cmd), res.returncode, res.stdout
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
@@ -61,9 +72,6 @@ def build_library(force=False, verbose=False):
         ok &= res.returncode == 0
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
         f.write("\n".join(log))
-    for r in results:
-        if os.path.exists(r[1]):
-            os.remove(r[1])
     if verbose or not ok:
         sys.stderr.write("\n".join(log)[-8000:])
     if not ok:

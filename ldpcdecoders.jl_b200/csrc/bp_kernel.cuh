@@ -65,6 +65,7 @@ struct KernelParams {
     uint8_t *conv;                // [B]
     int32_t *iters;               // [B] or null
     double *ratio;                // [B][n] or null
+    int ratio_last_only;          // 1: write ratios only in iteration max_iters
     unsigned long long *counters; // [4] or null
     // narrow tables (modes 0/1), copied to shared memory:
     const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
@@ -620,6 +621,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             unsigned long long flips = 0;
             uint32_t neww = 0;
             int delta = 0;
+            // posterior ratios: every iteration, or (ratio_last_only, the OSD pipeline) only in iteration max_iters --
+            // the only ratios belief_propagation_osd.jl:52 ever reads are those of syndromes that did not converge
+            const bool wr = p.ratio != nullptr && (!p.ratio_last_only || iter + 1 >= p.max_iters);
             // a lane walks its flipped variables (bits of f, first bit = variable index ibase)
             auto apply_flips = [&](unsigned long long f, int ibase) {
                 while (f) {
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             };
             // posterior ratio R of this lane's i-th variable j: optional output, hard decision (:163-168)
             auto record = [&](int j, int i, double R) {
-                if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
+                if (wr) p.ratio[sid * p.n + vorig_at(j)] = R;
                 const uint32_t bit = decide(R) ? 1u : 0u;                            // tie -> 1
                 if (use_regs) {
                     newbits |= static_cast<unsigned long long>(bit) << i;
@@ -784,13 +788,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 const double Rb = var_update<D>(mb, p0, regular_p0);                             \
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
-                if (p.ratio) { p.ratio[sid * p.n + j] = Ra; p.ratio[sid * p.n + j + W] = Rb; }   \
+                if (wr) { p.ratio[sid * p.n + j] = Ra; p.ratio[sid * p.n + j + W] = Rb; }   \
                 newbits |= static_cast<unsigned long long>((decide(Ra) ? 1u : 0u) | (decide(Rb) ? 2u : 0u)) << i; \
             }                                                                                    \
         }                                                                                        \
         for (; j < p.n; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
-            if (p.ratio) p.ratio[sid * p.n + j] = R;                                             \
+            if (wr) p.ratio[sid * p.n + j] = R;                                             \
             newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;               \
         }                                                                                        \
     }
@@ -802,7 +806,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                         const int deg = p.seg.vdeg[g], first = p.seg.vfirst[g], end = p.seg.vend[g], eb = p.seg.vedge[g];
                         if (deg == 0) {                                               // isolated variables: prior only
                             for (; j < end; j += W, ++i) {
-                                if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = p0;
+                                if (wr) p.ratio[sid * p.n + vorig_at(j)] = p0;
                                 newbits |= static_cast<unsigned long long>(decide(p0) ? 1u : 0u) << i;
                             }
                             continue;
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 const double Rb = var_update<D>(mb, p0, regular_p0);                             \
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
                 _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
-                if (p.ratio) {                                                                   \
+                if (wr) {                                                                   \
                     p.ratio[sid * p.n + vorig_at(j)] = Ra;                                       \
                     p.ratio[sid * p.n + vorig_at(j + W)] = Rb;                                   \
                 }                                                                                \
@@ -832,7 +836,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
         }                                                                                        \
         for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
             const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
-            if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;                                   \
+            if (wr) p.ratio[sid * p.n + vorig_at(j)] = R;                                   \
             newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;               \
         }                                                                                        \
     }
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                                             return *reinterpret_cast<double *>(msg_generic + off);
                                         },
                                         deg, p0);
-                                    if (p.ratio) p.ratio[sid * p.n + vorig_at(j)] = R;
+                                    if (wr) p.ratio[sid * p.n + vorig_at(j)] = R;
                                     newbits |= static_cast<unsigned long long>(decide(R) ? 1u : 0u) << i;
                                 }
                             })

@@ -21,6 +21,7 @@
 #include "bp_launch.h"
 #include "bp_math.cuh"
 #include "formats.cuh"
+#include "osd.cuh"
 
 namespace {
 
@@ -86,9 +87,10 @@ struct DeviceCtx {
     struct StageSet {
         cudaStream_t stream = nullptr;
         DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio;
+        DevBuf osd_list, osd_ctl;            // OSD-0: unconverged list, {count, queue}
     } set[2];
     cudaEvent_t decode_done = nullptr;
-    DevBuf counters, scratch;
+    DevBuf counters, scratch, osd_stats;
 };
 
 }  // namespace
@@ -113,6 +115,8 @@ struct ldpcb200 {
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
     double ms_scale = 0.875;     // min-sum normalisation factor (option "minsum_scale_permille")
+    int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
+    int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     // resolved configuration
     bool configured = false;
@@ -373,9 +377,10 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch}) b->release();
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats}) b->release();
     for (auto &S : d.set)
-        for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio}) b->release();
+        for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
+            b->release();
     if (d.decode_done) cudaEventDestroy(d.decode_done);
     if (d.set[1].stream) cudaStreamDestroy(d.set[1].stream);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -550,7 +555,8 @@ __global__ void add_counters_kernel(unsigned long long *c, unsigned long long de
 
 // Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
-                     uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st)
+                     uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st,
+                     bool ratio_last_only = false)
 {
     if (B <= 0) return 0;
     CU(cudaSetDevice(d.device));
@@ -576,6 +582,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     p.regular_p0 = h->regular_p0;
     p.check_aux = h->ms_scale;
     p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters; p.ratio = ratio;
+    p.ratio_last_only = ratio_last_only ? 1 : 0;
     p.counters = counters;
     p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
     p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
@@ -605,6 +612,77 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     return 0;
 }
 
+// ---- OSD-0 on the syndromes BP left unconverged (osd.cuh).  Stream-ordered; err_words is updated in place.
+constexpr int kOsdThreads = 256;
+
+int osd_layout(const ldpcb200 *h, bp::OsdParams &p)
+{
+    const int m = static_cast<int>(h->s), n = static_cast<int>(h->n);
+    int g = (n + 1 + 127) / 128;              // 16-byte groups per augmented row
+    if ((g & 1) == 0) ++g;                    // odd: 8 consecutive rows hit 8 distinct bank quads
+    p.m = m; p.n = n; p.NWr = 4 * g;
+    int np = 2;
+    while (np < n) np <<= 1;
+    p.NP = np;
+    p.SW = h->SW; p.NW = h->NW;
+    long long off = static_cast<long long>(m) * p.NWr * 4;
+    off = (off + 15) / 16 * 16;
+    p.off_key = static_cast<int>(off); off += static_cast<long long>(np) * 8;
+    p.off_idx = static_cast<int>(off); off += static_cast<long long>(np) * 4;
+    p.off_piv = static_cast<int>(off); off += static_cast<long long>(std::max(m, 1)) * 4 * 4;   // piv, prow, pcol, list
+    p.off_red = static_cast<int>(off); off += (16 + 192 + p.NWr / 4 + 1) * 4;
+    return off > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(off);
+}
+
+int osd0_on_device(ldpcb200 *h, DeviceCtx &d, DeviceCtx::StageSet &S, int64_t B, const uint32_t *syn_words,
+                   uint32_t *err_words, const uint8_t *conv, const double *ratio, unsigned long long *stats, cudaStream_t st)
+{
+    if (B <= 0) return 0;
+    if (h->variant != LDPCB200_VARIANT_EXACT)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD-0 is defined on the posterior ratios of the exact variant");
+    if (B > 0x7fffffffLL) return fail(LDPCB200_EINVAL, "OSD-0: at most 2^31-1 syndromes per call");
+    if (h->s > static_cast<int64_t>(bp::kOsdMaxRowsPerThread) * kOsdThreads)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD-0: more than %d checks", bp::kOsdMaxRowsPerThread * kOsdThreads);
+    CU(cudaSetDevice(d.device));
+    bp::OsdParams p{};
+    const int smem = osd_layout(h, p);
+    if (smem > d.smem_optin)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD-0: the bit-packed %lld x %lld matrix (%d bytes) does not fit in shared memory",
+                    static_cast<long long>(h->s), static_cast<long long>(h->n), smem);
+    int rc;
+    if ((rc = S.osd_list.reserve(static_cast<size_t>(B) * 4))) return rc;
+    if ((rc = S.osd_ctl.reserve(16))) return rc;
+    if (!stats) {
+        if ((rc = d.osd_stats.reserve(64))) return rc;
+        stats = d.osd_stats.as<unsigned long long>();
+    }
+    CU(cudaMemsetAsync(S.osd_ctl.p, 0, 16, st));
+    p.colptr = d.d_colptr; p.rowval = d.d_ve_chk;
+    p.syn_words = syn_words; p.err_words = err_words; p.ratio = ratio;
+    p.list = S.osd_list.as<int>(); p.count = S.osd_ctl.as<int>(); p.queue = S.osd_ctl.as<int>() + 1;
+    p.stats = stats;
+    p.profile = h->opt_osd_profile;
+    bp::osd_collect_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(conv, B, S.osd_list.as<int>(), S.osd_ctl.as<int>());
+    const int per_sm = std::max(1, std::min(4, d.smem_per_sm / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(d.sm_count) * per_sm));
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kOsdThreads, smem, st>>>(p);
+        return cudaSuccess;
+    };
+    switch ((p.m + kOsdThreads - 1) / kOsdThreads) {
+        case 0: case 1: CU(launch(bp::osd0_kernel<kOsdThreads, 1>)); break;
+        case 2: CU(launch(bp::osd0_kernel<kOsdThreads, 2>)); break;
+        case 3: CU(launch(bp::osd0_kernel<kOsdThreads, 3>)); break;
+        case 4: CU(launch(bp::osd0_kernel<kOsdThreads, 4>)); break;
+        default: CU(launch(bp::osd0_kernel<kOsdThreads, 8>)); break;
+    }
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 size_t fmt_bytes(int fmt, int64_t rows, int64_t ld, int64_t B, int RW)
 {
     switch (fmt) {
@@ -622,7 +700,7 @@ inline int grid_for(long long work, int sm) { return static_cast<int>(std::max<l
 // One device's share [b0, b0+Bd) of a host batch, processed in chunks.
 int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t Btot, const void *syndromes,
                       int syn_fmt, int64_t syn_ld, void *errors, int err_fmt, int64_t err_ld, uint8_t *converged,
-                      int32_t *iters, double *ratio, int64_t *counters_out)
+                      int32_t *iters, double *ratio, int64_t *counters_out, bool osd = false, int64_t *osd_stats_out = nullptr)
 {
     (void)Btot;
     CU(cudaSetDevice(d.device));
@@ -630,7 +708,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     // chunk size: bound the staging footprint (two sets are in flight)
     const double per_syn = static_cast<double>(fmt_bytes(syn_fmt, s, syn_ld, 2, h->SW) - fmt_bytes(syn_fmt, s, syn_ld, 1, h->SW)) +
                            static_cast<double>(fmt_bytes(err_fmt, n, err_ld, 2, h->NW) - fmt_bytes(err_fmt, n, err_ld, 1, h->NW)) +
-                           (h->SW + h->NW) * 4.0 + 5.0 + (ratio ? 8.0 * n : 0.0);
+                           (h->SW + h->NW) * 4.0 + 5.0 + ((ratio || osd) ? 8.0 * n : 0.0) + (osd ? 4.0 : 0.0);
     // about four chunks per call (every chunk ends with a tail of slow syndromes, so fewer is better, but
     // at least two are needed to overlap copies with decoding); never less than two waves of the
     // resident slots (a smaller chunk leaves SMs idle); staging bounded by 256 MB per set, or what
@@ -643,6 +721,10 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     int rc;
     if ((rc = d.counters.reserve(LDPCB200_NUM_COUNTERS * 8))) return rc;
     CU(cudaMemsetAsync(d.counters.p, 0, LDPCB200_NUM_COUNTERS * 8, d.set[0].stream));
+    if (osd) {
+        if ((rc = d.osd_stats.reserve(64))) return rc;
+        CU(cudaMemsetAsync(d.osd_stats.p, 0, 64, d.set[0].stream));
+    }
     CU(cudaStreamSynchronize(d.set[0].stream));
     bool have_prev_decode = false;
     int64_t chunk_no = 0;
@@ -656,7 +738,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         if ((rc = S.err_words.reserve(static_cast<size_t>(Bc) * h->NW * 4))) return rc;
         if ((rc = S.conv.reserve(static_cast<size_t>(Bc)))) return rc;
         if ((rc = S.iters.reserve(static_cast<size_t>(Bc) * 4))) return rc;
-        if (ratio && (rc = S.ratio.reserve(static_cast<size_t>(Bc) * n * 8))) return rc;
+        if ((ratio || osd) && (rc = S.ratio.reserve(static_cast<size_t>(Bc) * n * 8))) return rc;
         // ---- syndromes -> device -> packed rows
         uint32_t *syn_words = S.syn_words.as<uint32_t>();
         if (syn_fmt == LDPCB200_FMT_PACKED32) {
@@ -690,10 +772,20 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
         if (have_prev_decode) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
         rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
-                              ratio ? S.ratio.as<double>() : nullptr, d.counters.as<unsigned long long>(), st);
+                              (ratio || (osd && h->max_iters > 0)) ? S.ratio.as<double>() : nullptr,
+                              d.counters.as<unsigned long long>(), st, osd && !ratio);
         if (rc) return rc;
         CU(cudaEventRecord(d.decode_done, st));
         have_prev_decode = true;
+        if (osd) {
+            if (h->max_iters <= 0) {          // log_probabs stays zero (reset!, belief_propagation.jl:86): ratio 1 everywhere
+                bp::osd_fill_ones_kernel<<<grid_for(Bc * n, d.sm_count), 256, 0, st>>>(S.ratio.as<double>(), Bc * n);
+                h->launches++;
+            }
+            rc = osd0_on_device(h, d, S, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.ratio.as<double>(),
+                                d.osd_stats.as<unsigned long long>(), st);
+            if (rc) return rc;
+        }
         // ---- packed rows -> caller's format -> host
         const uint32_t *ew = S.err_words.as<uint32_t>();
         if (err_fmt == LDPCB200_FMT_PACKED32) {
@@ -741,6 +833,12 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     CU(cudaMemcpyAsync(hc, d.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int k = 0; k < LDPCB200_NUM_COUNTERS; ++k) counters_out[k] = static_cast<int64_t>(hc[k]);
+    if (osd && osd_stats_out) {
+        unsigned long long ho[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(ho, d.osd_stats.p, sizeof(ho), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int k = 0; k < LDPCB200_NUM_OSD_STATS; ++k) osd_stats_out[k] = static_cast<int64_t>(ho[k]);
+    }
     return 0;
 }
 
@@ -831,6 +929,8 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
 {
     if (!h || !key) return fail(LDPCB200_EINVAL, "null handle or key");
     const std::string k(key);
+    if (k == "osd_profile") { h->opt_osd_profile = value ? 1 : 0; return 0; }
+    if (k == "ratio_last_only") { h->opt_ratio_last_only = value ? 1 : 0; return 0; }
     if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration
     if (k == "chunk") { h->opt_chunk = value; return 0; }
     if (k == "minsum_scale_permille") { h->ms_scale = static_cast<double>(value) / 1000.0; return 0; }
@@ -876,14 +976,17 @@ int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uin
     if (rc) return rc;
     DeviceCtx &d = h->dev[dev_slot];
     return decode_on_device(h, d, B, d_syn_words, d_err_words, d_converged, d_iters, d_posterior_ratio, d_counters,
-                            stream ? static_cast<cudaStream_t>(stream) : d.stream);
+                            stream ? static_cast<cudaStream_t>(stream) : d.stream, h->opt_ratio_last_only != 0);
 }
 
-int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
-                          int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *posterior_ratio,
-                          int64_t *counters)
+static int decode_batch_impl(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
+                             int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *posterior_ratio,
+                             int64_t *counters, bool osd, int64_t *osd_stats)
 {
     if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (osd_stats) memset(osd_stats, 0, sizeof(int64_t) * LDPCB200_NUM_OSD_STATS);
+    if (osd && h->variant != LDPCB200_VARIANT_EXACT)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD-0 is defined on the posterior ratios of the exact variant");
     if (B < 0) return fail(LDPCB200_EINVAL, "negative batch");
     if (counters) memset(counters, 0, sizeof(int64_t) * LDPCB200_NUM_COUNTERS);
     if (B == 0) return 0;
@@ -903,10 +1006,12 @@ int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32
     std::vector<int> rcs(nd, 0);
     std::vector<std::string> errs(nd);
     std::vector<int64_t> ctr(static_cast<size_t>(nd) * LDPCB200_NUM_COUNTERS, 0);
+    std::vector<int64_t> ost(static_cast<size_t>(nd) * LDPCB200_NUM_OSD_STATS, 0);
     auto work = [&](int k) {
         if (lo[k + 1] > lo[k])
             rcs[k] = decode_host_range(h, h->dev[k], lo[k], lo[k + 1] - lo[k], B, syndromes, syn_fmt, syn_ld, errors, err_fmt,
-                                       err_ld, converged, iters, posterior_ratio, &ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS]);
+                                       err_ld, converged, iters, posterior_ratio, &ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS],
+                                       osd, &ost[static_cast<size_t>(k) * LDPCB200_NUM_OSD_STATS]);
         if (rcs[k]) errs[k] = g_err;
     };
     if (nd == 1) {
@@ -921,7 +1026,38 @@ int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32
     if (counters)
         for (int k = 0; k < nd; ++k)
             for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) counters[c] += ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS + c];
+    if (osd_stats)
+        for (int k = 0; k < nd; ++k)
+            for (int c = 0; c < LDPCB200_NUM_OSD_STATS; ++c) osd_stats[c] += ost[static_cast<size_t>(k) * LDPCB200_NUM_OSD_STATS + c];
     return 0;
+}
+
+int ldpcb200_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
+                          int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *posterior_ratio,
+                          int64_t *counters)
+{
+    return decode_batch_impl(h, B, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, posterior_ratio,
+                             counters, false, nullptr);
+}
+
+int ldpcb200_bposd_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
+                                int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, int64_t *counters,
+                                int64_t *osd_stats)
+{
+    return decode_batch_impl(h, B, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, nullptr, counters,
+                             true, osd_stats);
+}
+
+int ldpcb200_osd0_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_syn_words, uint32_t *d_err_words,
+                         const uint8_t *d_converged, const double *d_posterior_ratio, unsigned long long *d_stats, void *stream)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad dev_slot");
+    if (B < 0 || (B > 0 && (!d_syn_words || !d_err_words || !d_converged || !d_posterior_ratio)))
+        return fail(LDPCB200_EINVAL, "null device buffer");
+    DeviceCtx &d = h->dev[dev_slot];
+    return osd0_on_device(h, d, d.set[0], B, d_syn_words, d_err_words, d_converged, d_posterior_ratio, d_stats,
+                          stream ? static_cast<cudaStream_t>(stream) : d.stream);
 }
 
 int ldpcb200_sample_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, int64_t first, uint64_t seed, double per,

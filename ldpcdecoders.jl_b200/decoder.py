@@ -119,7 +119,20 @@ class BeliefPropagationDecoder:
         _lib.check(self._lib.ldpcb200_score_device(self._h, dev_slot, int(B), d_true_err_words,
                                                    d_err_words, d_syn_words, d_out, stream))
 
-    # -- raw host-buffer call ---------------------------------------------------------------
+    def osd0_device(self, B, d_syn_words, d_err_words, d_conv, d_ratio, d_stats=None, stream=None, dev_slot=0):
+        _lib.check(self._lib.ldpcb200_osd0_device(self._h, dev_slot, int(B), d_syn_words, d_err_words, d_conv,
+                                                  d_ratio, d_stats, stream))
+
+    # -- raw host-buffer calls --------------------------------------------------------------
+    def bposd_raw(self, B, syn, syn_fmt, syn_ld, err, err_fmt, err_ld, conv, iters=None):
+        counters = np.zeros(_lib.NUM_COUNTERS, dtype=np.int64)
+        stats = np.zeros(_lib.NUM_OSD_STATS, dtype=np.int64)
+        _lib.check(self._lib.ldpcb200_bposd_decode_batch(
+            self._h, int(B), syn.ctypes.data, syn_fmt, int(syn_ld), err.ctypes.data, err_fmt, int(err_ld),
+            conv.ctypes.data, iters.ctypes.data if iters is not None else None, counters.ctypes.data,
+            stats.ctypes.data))
+        return counters, stats
+
     def decode_raw(self, B, syn, syn_fmt, syn_ld, err, err_fmt, err_ld, conv, iters=None, ratio=None):
         counters = np.zeros(_lib.NUM_COUNTERS, dtype=np.int64)
         _lib.check(self._lib.ldpcb200_decode_batch(
@@ -129,8 +142,30 @@ class BeliefPropagationDecoder:
         return counters
 
 
+class BeliefPropagationOSDDecoder:
+    """Mirror of BeliefPropagationOSDDecoder(H, per, max_iters; osd_order=0)
+    (/root/reference/src/decoders/belief_propagation_osd.jl:17-29): fields bp_decoder, H, osd_order.
+    Only osd_order = 0 runs on the GPU (the path BASELINE config 4 names); higher orders are out of scope."""
+
+    def __init__(self, H, per, max_iters, osd_order=0, devices=None, **options):
+        if int(osd_order) != 0:
+            raise NotImplementedError("only osd_order = 0 is implemented on the GPU")
+        self.bp_decoder = BeliefPropagationDecoder(H, per, max_iters, devices=devices, **options)
+        self.H = H
+        self.osd_order = 0
+        self.s, self.n = self.bp_decoder.s, self.bp_decoder.n
+        self.last_counters = None
+        self.last_osd_stats = None
+
+    def close(self):
+        self.bp_decoder.close()
+
+
 def reset_b(decoder):
     """LDPCDecoders.reset!(decoder): the GPU path keeps no host scratch between calls."""
+    if isinstance(decoder, BeliefPropagationOSDDecoder):
+        reset_b(decoder.bp_decoder)
+        return decoder
     decoder.scratch.log_probabs[:] = 0.0
     decoder.scratch.err[:] = 0.0
     return decoder
@@ -172,8 +207,15 @@ def batchdecode_b(decoder, syndromes, errors, success=None, iters=None, posterio
         assert ratio.shape == (decoder.n, B) and ratio.dtype == np.float64 and ratio.flags.f_contiguous
     if iters is not None:
         assert iters.shape == (B,) and iters.dtype == np.int32
-    decoder.last_counters = decoder.decode_raw(B, syn_f, syn_fmt, max(decoder.s, 1), err_f, err_fmt,
-                                               max(decoder.n, 1), success.view(np.uint8), iters, ratio)
+    if isinstance(decoder, BeliefPropagationOSDDecoder):
+        # generic batchdecode! (abstract_decoder.jl:31-42) over decode!(::BeliefPropagationOSDDecoder)
+        if ratio is not None:
+            raise ValueError("posterior_ratio is not an output of the BP+OSD decoder")
+        decoder.last_counters, decoder.last_osd_stats = decoder.bp_decoder.bposd_raw(
+            B, syn_f, syn_fmt, max(decoder.s, 1), err_f, err_fmt, max(decoder.n, 1), success.view(np.uint8), iters)
+    else:
+        decoder.last_counters = decoder.decode_raw(B, syn_f, syn_fmt, max(decoder.s, 1), err_f, err_fmt,
+                                                   max(decoder.n, 1), success.view(np.uint8), iters, ratio)
     if err_f is not err:
         err[...] = err_f
     return errors, success
@@ -188,6 +230,13 @@ def decode_b(decoder, syndrome):
     if syn.dtype not in (np.bool_, np.uint8, np.int8, np.int64):
         syn = syn.astype(np.int64)
     syn_f = np.asfortranarray(syn.reshape(decoder.s, 1))
+    if isinstance(decoder, BeliefPropagationOSDDecoder):
+        # decode!(::BeliefPropagationOSDDecoder) returns a fresh Bool vector and BP's flag (:60)
+        out = np.zeros((decoder.n, 1), dtype=np.bool_, order="F")
+        conv = np.zeros(1, dtype=np.uint8)
+        decoder.last_counters, decoder.last_osd_stats = decoder.bp_decoder.bposd_raw(
+            1, syn_f, _fmt_of(syn_f, "syndrome"), max(decoder.s, 1), out, _lib.FMT_U8, max(decoder.n, 1), conv)
+        return out[:, 0], bool(conv[0])
     err = decoder.scratch.err.reshape(decoder.n, 1, order="F")
     conv = np.zeros(1, dtype=np.uint8)
     ratio = None

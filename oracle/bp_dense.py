@@ -81,3 +81,57 @@ def brute_force_ratio(H, per, syndrome):
         p0 += pr * (1 - e)
     with np.errstate(all="ignore"):
         return p1 / p0
+
+
+def osd0_dense(H, syndrome, bp_err, ratio):
+    """Dense transliteration of decode!(::BeliefPropagationOSDDecoder) after the BP call
+    (belief_propagation_osd.jl:52-60) and of osd(..., Val(0)) (:63-125), numpy bool matrices, physical
+    row swaps, same loop order.  r = 1/R replaces exp(log(1/R)) exactly as in bp_oracle.c.
+    Also the mathematical characterisation used to double check it: see osd0_by_definition."""
+    H = np.asarray(H).astype(bool)
+    m, n = H.shape
+    with np.errstate(all="ignore"):
+        r = np.float64(1.0) / np.asarray(ratio, dtype=np.float64)
+        key = np.maximum(r, np.float64(1.0) - r)
+    order = sorted(range(n), key=lambda j: (-key[j], j))          # stable sortperm(..., rev=true)
+    Hs = H[:, order].copy()
+    e = np.asarray(bp_err).astype(np.int64)[order]
+    t = np.asarray(syndrome).astype(bool).copy()                  # :66
+    for j in range(n):
+        if e[j] == 1:
+            t ^= Hs[:, j]
+    if not t.any():
+        corr = e.astype(bool)
+    else:
+        Hw = Hs.copy()
+        rows, cols = [], []
+        i = 0
+        for j in range(n):
+            if i >= m or not t[i:].any():
+                break
+            nz = np.nonzero(Hw[i:, j])[0]
+            if nz.size:
+                k = int(nz[0])
+                if e[j] == 1:
+                    t ^= Hw[:, j]
+                if k > 0:
+                    ii = i + k
+                    Hw[[i, ii], :] = Hw[[ii, i], :]
+                    t[i], t[ii] = t[ii], t[i]
+                for ii in range(i + 1, m):
+                    if Hw[ii, j]:
+                        Hw[ii, :] ^= Hw[i, :]
+                        t[ii] ^= t[i]
+                rows.append(i)
+                cols.append(j)
+                i += 1
+        corr = e.astype(bool).copy()
+        for rr, c in zip(rows[::-1], cols[::-1]):
+            corr[c] = t[rr]
+            if corr[c]:
+                for ii in range(rr):
+                    if Hw[ii, c]:
+                        t[ii] ^= True
+    out = np.zeros(n, dtype=np.uint8)
+    out[np.asarray(order)] = corr.astype(np.uint8)
+    return out

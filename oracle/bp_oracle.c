@@ -410,3 +410,154 @@ int bp_oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------
+ * OSD-0 post-processing, the consumer of the BP stage in BASELINE config 4:
+ * decode!(::BeliefPropagationOSDDecoder, syndrome)  belief_propagation_osd.jl:49-61 and
+ * osd(H, syndrome, bp_err, Val(0))                  belief_propagation_osd.jl:63-125.
+ * Control flow follows the reference statement by statement (physical row swaps, the early
+ * break on an all-zero remaining target, the reverse back-substitution); rows of H_work are
+ * bit-packed (uint64 words over the SORTED column positions), which changes no result.
+ *
+ * One stated deviation: the reference sorts on max(r, 1-r) with r = exp(log_probabs) and
+ * log_probabs = log(1/R) (belief_propagation.jl:163, belief_propagation_osd.jl:52-55), using
+ * Julia's own exp/log.  Those cannot be reproduced bit for bit here, so r = RN(1/R) is used
+ * (the value exp(log(.)) approximates to a few ulp).  The order can differ from Julia's only
+ * between two posteriors that agree to ~2^-45 relative without being equal; exact ties (the
+ * common case, by symmetry) are broken by index exactly as Julia's stable sortperm does.
+ * PARITY UNPINNED like the rest of this file.
+ * ------------------------------------------------------------------------------------ */
+typedef struct { double key; int64_t idx; } keyidx_t;
+
+static int cmp_keyidx_desc(const void *a, const void *b)
+{
+    const keyidx_t *x = (const keyidx_t *)a, *y = (const keyidx_t *)b;
+    if (x->key > y->key) return -1;           /* rev=true: larger key first              */
+    if (x->key < y->key) return 1;
+    return (x->idx > y->idx) - (x->idx < y->idx);   /* stable: equal keys keep index order */
+}
+
+#define OSD_BIT(row, j) (((row)[(j) >> 6] >> ((j) & 63)) & 1ull)
+
+static int osd0_one(const graph_t *g, const int64_t *colptr, const int64_t *rowval,
+                    const uint8_t *syn, const uint8_t *bp_err, const double *ratio,
+                    uint8_t *out, keyidx_t *ki, uint64_t *Hw, uint8_t *tgt,
+                    uint8_t *err_sorted, uint8_t *corr, int64_t *piv_r, int64_t *piv_c)
+{
+    const int64_t m = g->s, n = g->n, nw = (n + 63) / 64;
+    /* :53-55  reliability order */
+    for (int64_t j = 0; j < n; ++j) {
+        double r = 1.0 / ratio[j];
+        double q = 1.0 - r;
+        ki[j].key = (r > q) ? r : q;
+        ki[j].idx = j;
+    }
+    qsort(ki, (size_t)n, sizeof(keyidx_t), cmp_keyidx_desc);
+    /* :56-57  H_sorted (bit-packed rows), bp_err_sorted */
+    memset(Hw, 0, sizeof(uint64_t) * (size_t)(m * nw));
+    for (int64_t j = 0; j < n; ++j) {
+        int64_t c = ki[j].idx;
+        err_sorted[j] = bp_err[c];
+        for (int64_t e = colptr[c]; e < colptr[c + 1]; ++e)
+            Hw[rowval[e] * nw + (j >> 6)] |= 1ull << (j & 63);
+    }
+    /* :66-71  s_target = syndrome xor H*bp_err */
+    for (int64_t i = 0; i < m; ++i) tgt[i] = syn[i] & 1;
+    for (int64_t j = 0; j < n; ++j)
+        if (err_sorted[j] == 1)
+            for (int64_t i = 0; i < m; ++i) tgt[i] ^= (uint8_t)OSD_BIT(Hw + i * nw, j);
+    int any = 0;
+    for (int64_t i = 0; i < m; ++i) any |= tgt[i];
+    memcpy(corr, err_sorted, (size_t)n);
+    int64_t np = 0;
+    if (any) {                                   /* :72-74 returns bp_err otherwise */
+        int64_t i = 0;
+        for (int64_t j = 0; j < n; ++j) {        /* :81-107 */
+            if (i >= m) break;
+            int rest = 0;
+            for (int64_t ii = i; ii < m; ++ii) rest |= tgt[ii];
+            if (!rest) break;
+            int64_t k = -1;
+            for (int64_t ii = i; ii < m; ++ii) if (OSD_BIT(Hw + ii * nw, j)) { k = ii; break; }
+            if (k < 0) continue;
+            if (err_sorted[j] == 1)
+                for (int64_t ii = 0; ii < m; ++ii) tgt[ii] ^= (uint8_t)OSD_BIT(Hw + ii * nw, j);
+            if (k != i) {
+                for (int64_t w = 0; w < nw; ++w) {
+                    uint64_t t = Hw[i * nw + w]; Hw[i * nw + w] = Hw[k * nw + w]; Hw[k * nw + w] = t;
+                }
+                uint8_t t = tgt[i]; tgt[i] = tgt[k]; tgt[k] = t;
+            }
+            for (int64_t ii = i + 1; ii < m; ++ii)
+                if (OSD_BIT(Hw + ii * nw, j)) {
+                    for (int64_t w = 0; w < nw; ++w) Hw[ii * nw + w] ^= Hw[i * nw + w];
+                    tgt[ii] ^= tgt[i];
+                }
+            piv_r[np] = i; piv_c[np] = j; ++np;
+            ++i;
+        }
+        for (int64_t q = np - 1; q >= 0; --q) {  /* :110-121 */
+            int64_t r = piv_r[q], c = piv_c[q];
+            corr[c] = tgt[r];
+            if (corr[c])
+                for (int64_t ii = 0; ii < r; ++ii)
+                    if (OSD_BIT(Hw + ii * nw, c)) tgt[ii] ^= 1;
+        }
+    }
+    for (int64_t j = 0; j < n; ++j) out[ki[j].idx] = corr[j];   /* :60 err[invperm(...)] */
+    return (int)np;
+}
+
+/* BP followed by OSD-0 on every column of the batch (decode! of the BP+OSD decoder applied per
+ * column).  err: n x B bytes out (the OSD result), conv: BP's converged flag (:60), bp_err:
+ * optional n x B bytes (BP's own decisions), pivots: optional B int32 (pivots used). */
+int bp_oracle_bposd_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                          double per, int32_t max_iters, int64_t B, const uint8_t *syn,
+                          uint8_t *err, uint8_t *conv, uint8_t *bp_err_out, int32_t *pivots,
+                          int32_t nthreads)
+{
+    graph_t g;
+    int rc = build_graph(&g, s, n, colptr, rowval);
+    if (rc) return rc;
+    if (nthreads < 1) nthreads = 1;
+    int fail = 0;
+    const size_t nn = (size_t)(n ? n : 1), ss = (size_t)(s ? s : 1), nw = (size_t)((n + 63) / 64 + 1);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        size_t msz = g.E ? (size_t)g.E : 1;
+        double *a = (double *)malloc(sizeof(double) * msz), *b = (double *)malloc(sizeof(double) * msz);
+        double *ratio = (double *)malloc(sizeof(double) * nn);
+        uint8_t *bp = (uint8_t *)malloc(nn), *tgt = (uint8_t *)malloc(ss);
+        uint8_t *es = (uint8_t *)malloc(nn), *corr = (uint8_t *)malloc(nn);
+        keyidx_t *ki = (keyidx_t *)malloc(sizeof(keyidx_t) * nn);
+        uint64_t *Hw = (uint64_t *)malloc(sizeof(uint64_t) * ss * nw);
+        int64_t *pr = (int64_t *)malloc(sizeof(int64_t) * ss), *pc = (int64_t *)malloc(sizeof(int64_t) * ss);
+        if (!a || !b || !ratio || !bp || !tgt || !es || !corr || !ki || !Hw || !pr || !pc) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            fail = 1;
+        } else {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+            for (int64_t c = 0; c < B; ++c) {
+                const uint8_t *sc = syn + (size_t)c * (size_t)s;
+                int32_t itc = 0;
+                int cv = decode_edge(&g, per, max_iters, sc, a, b, bp, ratio, &itc);
+                conv[c] = (uint8_t)cv;
+                if (bp_err_out) memcpy(bp_err_out + (size_t)c * (size_t)n, bp, (size_t)n);
+                int np = 0;
+                /* max_iters = 0 leaves log_probabs = 0, i.e. ratio 1 everywhere (decode_edge does that) */
+                np = osd0_one(&g, colptr, rowval, sc, bp, ratio, err + (size_t)c * (size_t)n,
+                              ki, Hw, tgt, es, corr, pr, pc);
+                if (pivots) pivots[c] = np;
+            }
+        }
+        free(a); free(b); free(ratio); free(bp); free(tgt); free(es); free(corr); free(ki); free(Hw); free(pr); free(pc);
+    }
+    free_graph(&g);
+    return fail ? -1 : 0;
+}

@@ -45,6 +45,10 @@ def load():
     lib.bp_oracle_sample.restype = ctypes.c_int
     lib.bp_oracle_sample.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double,
                                      ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, u8p, u8p]
+    lib.bp_oracle_bposd_batch.restype = ctypes.c_int
+    lib.bp_oracle_bposd_batch.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double,
+                                          ctypes.c_int32, ctypes.c_int64, u8p, u8p, u8p, u8p,
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
     lib.bp_oracle_set_minsum_scale.argtypes = [ctypes.c_double]
     lib.bp_oracle_set_minsum_scale.restype = None
     lib.bp_oracle_threshold.restype = ctypes.c_uint32
@@ -98,6 +102,30 @@ def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_rat
     if want_ratio:
         out["ratio"] = ratio
     return out
+
+
+def bposd_decode(H, per, max_iters, syndromes, nthreads=1):
+    """Restated decode!(::BeliefPropagationOSDDecoder, syndrome) with osd_order = 0
+    (belief_propagation_osd.jl:49-125) applied to every column.  Returns dict(errors (n,B) uint8 -- the
+    OSD result, converged (B,) bool -- BP's flag, bp_errors (n,B) uint8, pivots (B,) int32)."""
+    lib = load()
+    s, n, colptr, rowval = csc_arrays(H)
+    syn = np.asfortranarray(np.asarray(syndromes).astype(np.uint8))
+    if syn.ndim == 1:
+        syn = np.asfortranarray(syn.reshape(s, 1))
+    assert syn.shape[0] == s
+    B = syn.shape[1]
+    err = np.zeros((n, B), dtype=np.uint8, order="F")
+    bp = np.zeros((n, B), dtype=np.uint8, order="F")
+    conv = np.zeros(B, dtype=np.uint8)
+    piv = np.zeros(B, dtype=np.int32)
+    rc = lib.bp_oracle_bposd_batch(s, n, _p(colptr, ctypes.c_int64), _p(rowval, ctypes.c_int64),
+                                   float(per), int(max_iters), B, _p(syn, ctypes.c_uint8),
+                                   _p(err, ctypes.c_uint8), _p(conv, ctypes.c_uint8), _p(bp, ctypes.c_uint8),
+                                   _p(piv, ctypes.c_int32), int(nthreads))
+    if rc != 0:
+        raise RuntimeError("bp_oracle_bposd_batch failed: %d" % rc)
+    return dict(errors=err, converged=conv.astype(bool), bp_errors=bp, pivots=piv)
 
 
 def sample(H, per, seed, first, B):

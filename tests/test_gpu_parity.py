@@ -419,3 +419,72 @@ def test_minsum_quality_is_close_to_sum_product(pkg, oracle, codes):
     ok_sp = (sp["errors"] == errs).all(axis=0).mean()
     assert ok_ms > ok_sp - 0.01, (ok_ms, ok_sp)
     assert ms["converged"].mean() > 0.97
+
+
+# ---------------------------------------------------------------------------------------------
+# BP + OSD-0 (reference belief_propagation_osd.jl:49-125) -- GPU Gauss-Jordan
+# without row swaps against the literal restatement (row swaps, early break, back substitution)
+def run_gpu_bposd(pkg, H, per, max_iters, syn, fmt=np.uint8, **opts):
+    dec = pkg.BeliefPropagationOSDDecoder(H, per, max_iters, **opts)
+    n, B = H.shape[1], syn.shape[1]
+    errors = np.full((n, B), 1, dtype=fmt, order="F")
+    _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn.astype(fmt)), errors)
+    out = dict(errors=errors.astype(np.uint8), converged=success.copy(), counters=dec.last_counters.copy(),
+               stats=dec.last_osd_stats.copy())
+    dec.close()
+    return out
+
+
+@pytest.mark.parametrize("name,per,B", [("C3", 0.06, 3000), ("C3", 0.12, 1500), ("C2", 0.05, 2000), ("C4", 0.04, 300),
+                                        ("C4", 0.08, 150), ("C1", 0.09, 60)])
+def test_bposd_matches_restated_reference(pkg, oracle, codes, name, per, B):
+    H, _, mi = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 4242, 0, B)
+    ref = oracle.bposd_decode(H, per, mi, syn, nthreads=oracle.num_threads())
+    g = run_gpu_bposd(pkg, H, per, mi, syn)
+    nonconv = int((~ref["converged"]).sum())
+    assert nonconv > 0, "case does not exercise OSD"
+    assert np.array_equal(g["converged"], ref["converged"])
+    bad = np.nonzero((g["errors"] != ref["errors"]).any(axis=0))[0]
+    assert bad.size == 0, "OSD results differ on syndromes %s (%d unconverged of %d)" % (bad[:10], nonconv, B)
+    assert g["stats"][0] == nonconv
+    assert g["stats"][1] == int(ref["pivots"].sum())
+    # OSD-0 always returns an error that reproduces the syndrome when the syndrome is in the column space
+    Hd = np.asarray(sp.csc_matrix(H).todense()).astype(np.int64)
+    assert np.array_equal((Hd @ g["errors"].astype(np.int64)) % 2, syn.astype(np.int64))
+
+
+def test_bposd_edge_cases(pkg, oracle, codes):
+    H, _, _ = codes.config_matrix("C3")
+    _, syn = oracle.sample(H, 0.08, 99, 0, 257)
+    # max_iters = 0: BP returns zeros / not converged, log_probabs = 0 -> all keys tie -> index order
+    for mi in (0, 1, 3):
+        ref = oracle.bposd_decode(H, 0.08, mi, syn, nthreads=2)
+        g = run_gpu_bposd(pkg, H, 0.08, mi, syn)
+        assert np.array_equal(g["converged"], ref["converged"])
+        assert np.array_equal(g["errors"], ref["errors"])
+    # int64 matrices (Matrix{Int}) and the single-syndrome decode!
+    ref = oracle.bposd_decode(H, 0.08, 8, syn, nthreads=2)
+    g = run_gpu_bposd(pkg, H, 0.08, 8, syn, fmt=np.int64)
+    assert np.array_equal(g["errors"], ref["errors"])
+    dec = pkg.BeliefPropagationOSDDecoder(H, 0.08, 8)
+    for b in (0, 5, 100):
+        e, conv = pkg.decode_b(dec, syn[:, b])
+        assert e.dtype == np.bool_ and np.array_equal(e.astype(np.uint8), ref["errors"][:, b]) and conv == ref["converged"][b]
+    assert pkg.reset_b(dec) is dec
+    dec.close()
+    # a syndrome outside the column space (rank-deficient H with a redundant check violated): the reference
+    # runs out of columns and returns whatever the elimination solved; same here
+    Hs = np.asarray(sp.csc_matrix(codes.surface_x(5)).todense()).astype(np.uint8)
+    Hr = np.vstack([Hs, Hs[0:1] ^ Hs[1:2]])            # last row = row0 + row1
+    rng = np.random.default_rng(5)
+    synr = (rng.random((Hr.shape[0], 64)) < 0.3).astype(np.uint8)
+    ref = oracle.bposd_decode(Hr, 0.05, 6, synr, nthreads=2)
+    g = run_gpu_bposd(pkg, Hr, 0.05, 6, synr)
+    assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
+    # min-sum posteriors are LLRs: OSD is refused, loudly
+    decm = pkg.BeliefPropagationDecoder(H, 0.05, 8, variant="minsum")
+    with pytest.raises(pkg._lib.LibraryError):
+        decm.bposd_raw(1, np.zeros((72, 1), np.uint8, order="F"), pkg._lib.FMT_U8, 72, np.zeros((144, 1), np.uint8, order="F"),
+                       pkg._lib.FMT_U8, 144, np.zeros(1, np.uint8))
+    decm.close()

@@ -51,3 +51,24 @@ if his:
         print("  %-10s %14d %5.1f%%" % (k, v, 100.0 * v / tot))
     fp64 = sum(v for k, v in agg.items() if k in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"))
     print("  FP64-pipe share of issued instructions: %.1f%%" % (100.0 * fp64 / tot))
+    # per-instruction stall samples (SASS listing with sample counts; top lines first)
+    col = next((c for c in ("Warp Stall Sampling (All Samples)", "Warp Stall Sampling (All Cycles)", "# Samples") if c in ix), None)
+    if col and len(sys.argv) > 2:
+        lines = []
+        for k, x in enumerate(body):
+            if len(x) < len(h):
+                continue
+            try:
+                sm = int(x[ix[col]])
+            except ValueError:
+                sm = 0
+            lines.append((k, sm, x[ix["Source"]]))
+        tots = sum(l[1] for l in lines) or 1
+        with open(sys.argv[2], "w") as f:
+            f.write("# SASS listing with %s (total %d)\n" % (col, tots))
+            for k, sm, src_ in lines:
+                f.write("%5d %7d %5.1f%%  %s\n" % (k, sm, 100.0 * sm / tots, src_))
+        print("-" * 100)
+        print("top instructions by %s:" % col)
+        for k, sm, src_ in sorted(lines, key=lambda l: -l[1])[:30]:
+            print("  #%-5d %7d %5.1f%%  %s" % (k, sm, 100.0 * sm / tots, src_))
