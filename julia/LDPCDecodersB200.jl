@@ -4,7 +4,8 @@
 # ldpcdecoders.jl_b200/decoder.py drives exactly the same C entry points and is what the tests
 # exercise.  Drop this file next to LDPCDecoders.jl and `include` it after the package: it adds a
 # GPU decoder type with the reference's constructor / decode! / batchdecode! / reset! methods
-# (src/decoders/belief_propagation.jl:61-67, 83-91, 121-188, 220-231).
+# (src/decoders/belief_propagation.jl:61-67, 83-91, 121-188, 220-231), and the BP+OSD decoder with osd_order = 0
+# (src/decoders/belief_propagation_osd.jl:17-125).
 module LDPCDecodersB200
 
 using SparseArrays
@@ -114,6 +115,55 @@ function decode!(dec::B200BeliefPropagationDecoder, syndrome::AbstractVector)
     end
     dec.scratch.log_probabs .= log.(1 ./ ratio)        # belief_propagation.jl:163, Julia's own log
     return dec.scratch.err, conv[1]
+end
+
+# ---- BP + OSD-0  (src/decoders/belief_propagation_osd.jl:17-61; osd(..., Val(0)) :63-125) -------------
+"""
+    B200BeliefPropagationOSDDecoder(H, per::Float64, max_iters::Int; osd_order::Int=0)
+
+Same fields as `BeliefPropagationOSDDecoder` (belief_propagation_osd.jl:17-24).  Only `osd_order = 0` is
+implemented on the GPU; BP and the OSD-0 elimination of the unconverged syndromes run in one library call.
+"""
+struct B200BeliefPropagationOSDDecoder <: AbstractDecoder
+    bp_decoder::B200BeliefPropagationDecoder
+    H::BitMatrix
+    osd_order::Int
+end
+
+function B200BeliefPropagationOSDDecoder(H, per::Float64, max_iters::Int; osd_order::Int=0, kw...)
+    osd_order == 0 || error("B200BeliefPropagationOSDDecoder: only osd_order = 0 runs on the GPU")
+    return B200BeliefPropagationOSDDecoder(B200BeliefPropagationDecoder(H, per, max_iters; kw...), BitMatrix(H), 0)
+end
+
+reset!(dec::B200BeliefPropagationOSDDecoder) = (reset!(dec.bp_decoder); dec)
+
+# generic batchdecode! (abstract_decoder.jl:31-42) over decode!(::BeliefPropagationOSDDecoder), done in one call
+function batchdecode!(dec::B200BeliefPropagationOSDDecoder, syndromes::AbstractMatrix, errors::AbstractMatrix,
+                      converged::AbstractVector{Bool})
+    @assert size(syndromes, 2) == size(errors, 2)
+    @assert size(syndromes, 2) == length(converged)
+    bp = dec.bp_decoder
+    B = size(syndromes, 2)
+    syn = syndromes isa Union{BitMatrix,Matrix{Bool},Matrix{UInt8},Matrix{Int64}} ? syndromes : Matrix{Int64}(syndromes)
+    err = errors isa Union{BitMatrix,Matrix{Bool},Matrix{UInt8},Matrix{Int64},Matrix{Float64}} ? errors : Matrix{Int64}(undef, bp.n, B)
+    conv = converged isa Vector{Bool} ? converged : Vector{Bool}(undef, B)
+    GC.@preserve syn err conv begin
+        check(ccall((:ldpcb200_bposd_decode_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Int64, Ptr{Cvoid}, Int32, Int64, Ptr{UInt8}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
+                    bp.handle, B, hostptr(syn), fmt_of(syn), bp.s, hostptr(err), fmt_of(err), bp.n,
+                    pointer(conv), C_NULL, C_NULL, C_NULL))
+    end
+    err === errors || (errors .= err)
+    conv === converged || (converged .= conv)
+    return errors, converged
+end
+
+# decode! returns a fresh Bool vector and BP's converged flag (belief_propagation_osd.jl:60)
+function decode!(dec::B200BeliefPropagationOSDDecoder, syndrome::AbstractVector)
+    errors = Matrix{Bool}(undef, dec.bp_decoder.n, 1)
+    conv = Vector{Bool}(undef, 1)
+    batchdecode!(dec, reshape(Vector{Int64}(syndrome), dec.bp_decoder.s, 1), errors, conv)
+    return vec(errors), conv[1]
 end
 
 end # module

@@ -169,3 +169,56 @@ def test_minsum_definition_sanity(oracle, codes):
     assert np.array_equal(a["errors"], b["errors"]) and np.array_equal(a["ratio"], b["ratio"], equal_nan=True)
     ok = (np.asarray((H @ a["errors"]) % 2) == syn).all(axis=0)
     assert np.array_equal(ok, a["converged"])
+
+
+# ---- OSD-0 restatement (belief_propagation_osd.jl:49-125) -------------------------------------
+def _gf2_rank(M):
+    M = (np.asarray(M) % 2).astype(np.uint8).copy()
+    r = 0
+    for c in range(M.shape[1]):
+        nz = np.nonzero(M[r:, c])[0]
+        if nz.size == 0:
+            continue
+        M[[r, r + nz[0]]] = M[[r + nz[0], r]]
+        for i in np.nonzero(M[:, c])[0]:
+            if i != r:
+                M[i] ^= M[r]
+        r += 1
+        if r == M.shape[0]:
+            break
+    return r
+
+
+@pytest.mark.parametrize("name,per,mi,B", [("C3", 0.08, 8, 80), ("C2", 0.08, 6, 40)])
+def test_osd0_c_restatement_equals_dense_transliteration(oracle, codes, name, per, mi, B):
+    from oracle import bp_dense
+    H, _, _ = codes.config_matrix(name)
+    Hd = np.asarray(H.todense()).astype(np.uint8)
+    _, syn = oracle.sample(H, per, 31337, 0, B)
+    out = oracle.bposd_decode(H, per, mi, syn, nthreads=2)
+    bp = oracle.batch_decode(H, per, mi, syn, want_ratio=True)
+    assert np.array_equal(out["bp_errors"], bp["errors"]) and np.array_equal(out["converged"], bp["converged"])
+    assert (~out["converged"]).sum() > 5
+    for b in range(B):
+        ref = bp_dense.osd0_dense(Hd, syn[:, b], bp["errors"][:, b], bp["ratio"][:, b])
+        assert np.array_equal(ref, out["errors"][:, b]), b
+    # converged syndromes come back untouched (:72-74); every output reproduces its syndrome
+    cv = out["converged"]
+    assert np.array_equal(out["errors"][:, cv], bp["errors"][:, cv])
+    assert np.array_equal((Hd.astype(np.int64) @ out["errors"].astype(np.int64)) % 2, syn.astype(np.int64))
+    # the pivots never exceed the rank, threads do not change results
+    assert out["pivots"].max() <= _gf2_rank(Hd)
+    assert np.array_equal(oracle.bposd_decode(H, per, mi, syn, nthreads=1)["errors"], out["errors"])
+
+
+def test_osd0_reference_testset_properties(oracle, codes):
+    """What the reference's own BP+OSD tests pin (test/test_bposd_decoder.jl): the OSD output always
+    satisfies the syndrome, also where BP alone fails, and equals BP's output where BP converged."""
+    H = codes.gallager(120, 6, 3, seed=11)
+    Hd = np.asarray(H.todense()).astype(np.int64)
+    _, syn = oracle.sample(H, 0.09, 5, 0, 200)
+    out = oracle.bposd_decode(H, 0.09, 10, syn, nthreads=2)
+    assert (~out["converged"]).sum() > 10
+    assert np.array_equal((Hd @ out["errors"].astype(np.int64)) % 2, syn.astype(np.int64))
+    bp_ok = ((Hd @ out["bp_errors"].astype(np.int64)) % 2 == syn).all(axis=0)
+    assert np.array_equal(bp_ok, out["converged"])
