@@ -552,6 +552,20 @@ def main():
                  "bposd_exact_match_frac": float(sc_osd[0].item()) / Bo,
                  "bposd_syndrome_satisfied_frac": float(sc_osd[1].item()) / Bo,
                  "note": "device-resident; the BP stage writes posterior ratios only in iteration max_iters (ratio_last_only)"}
+        if not args.no_e2e:
+            # the reference-facing call: host arrays in, host arrays out (ldpcb200_bposd_decode_batch)
+            import time as _t
+            syn_h = synw[:Bo].cpu().numpy().view(np.uint32)
+            err_h = np.zeros((Bo, NW), dtype=np.uint32)
+            conv_h = np.zeros(Bo, dtype=np.uint8)
+            dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
+            t0 = _t.perf_counter()
+            for _ in range(reps):
+                dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
+            dt = _t.perf_counter() - t0
+            bposd["e2e"] = {"value": Bo * reps / dt, "unit": UNIT, "h2d_bytes_per_step": int(Bo * SW * 4),
+                            "d2h_bytes_per_step": int(Bo * (NW * 4 + 1)),
+                            "api": "ldpcb200_bposd_decode_batch(FMT_PACKED32 in/out, host buffers), wall clock"}
         if not args.no_cpu:
             import time as _t
             oracle = entry.load_oracle()

@@ -488,3 +488,57 @@ def test_bposd_edge_cases(pkg, oracle, codes):
         decm.bposd_raw(1, np.zeros((72, 1), np.uint8, order="F"), pkg._lib.FMT_U8, 72, np.zeros((144, 1), np.uint8, order="F"),
                        pkg._lib.FMT_U8, 144, np.zeros(1, np.uint8))
     decm.close()
+
+
+def test_bposd_large_batch_properties_and_host_device_agreement(pkg, oracle, codes):
+    """200k gross-code syndromes at per = 0.08 (a third unconverged): the chunked host entry point (two staging sets,
+    two streams) and the device-resident BP -> OSD-0 pipeline give the same bits; converged flags are BP's; every
+    output reproduces its syndrome; converged rows are BP's own decisions; a sample equals the restated reference."""
+    H, _, mi = codes.config_matrix("C3")
+    s, n = H.shape
+    per, B = 0.08, 200_000
+    dec = pkg.BeliefPropagationOSDDecoder(H, per, mi, chunk=32768)
+    bp = dec.bp_decoder
+    info = bp.info()
+    SW, NW = info["syn_words"], info["err_words"]
+    dev = torch.device("cuda:0")
+    truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
+    bp.sample_device(B, 0, 777, per, truth.data_ptr(), synw.data_ptr())
+    torch.cuda.synchronize()
+    # host entry point, native packed rows
+    syn_h = synw.cpu().numpy().view(np.uint32)
+    err_h = np.zeros((B, NW), dtype=np.uint32)
+    conv_h = np.zeros(B, dtype=np.uint8)
+    ctr, stats = bp.bposd_raw(B, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
+    # device pipeline
+    errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    bperr = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    conv = torch.empty(B, dtype=torch.uint8, device=dev)
+    ratio = torch.empty((B, n), dtype=torch.float64, device=dev)
+    st8 = torch.zeros(8, dtype=torch.int64, device=dev)
+    score = torch.zeros(2, dtype=torch.int64, device=dev)
+    bp.set_option("ratio_last_only", 1)
+    bp.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), None, ratio.data_ptr(), None)
+    torch.cuda.synchronize()
+    bperr.copy_(errw)
+    bp.osd0_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), ratio.data_ptr(), st8.data_ptr())
+    bp.score_device(B, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), score.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(errw.cpu().numpy().view(np.uint32), err_h)
+    assert np.array_equal(conv.cpu().numpy(), conv_h)
+    nonconv = int((conv == 0).sum().item())
+    assert 0.1 * B < nonconv < 0.9 * B
+    assert stats[0] == nonconv == int(st8[0].item()) and stats[1] == int(st8[1].item())
+    assert ctr[0] == B and ctr[1] == B - nonconv
+    assert int(score[1].item()) == B                       # H * e == syndrome for every syndrome after OSD-0
+    cm = conv.bool()
+    assert torch.equal(errw[cm], bperr[cm])                # converged: BP's own decision (:72-74)
+    assert not torch.equal(errw[~cm], bperr[~cm])
+    for first, cnt in ((0, 300), (150_000, 200)):
+        _, s_ref = oracle.sample(H, per, 777, first, cnt)
+        ref = oracle.bposd_decode(H, per, mi, s_ref, nthreads=oracle.num_threads())
+        got = np.unpackbits(err_h[first:first + cnt].view(np.uint8), axis=1, bitorder="little")[:, :n].T
+        assert np.array_equal(got, ref["errors"])
+        assert np.array_equal(conv_h[first:first + cnt].astype(bool), ref["converged"])
+    dec.close()
