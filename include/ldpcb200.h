@@ -107,6 +107,8 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   "minsum_scale_permille" (min-sum variant: normalisation factor x 1000, default 875),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk),
+ *   "small_batch" (batches of at most this many syndromes run on the node-parallel kernel, one CTA per syndrome:
+ *   the low-latency path of decode!; -1 = number of SMs (default), 0 = never),
  *   "ratio_last_only" (ldpcb200_decode_device writes d_posterior_ratio only in iteration max_iters: all an OSD
  *   stage needs, since it only reads the ratios of syndromes that did not converge; default 0). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);

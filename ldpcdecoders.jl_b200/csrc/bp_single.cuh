@@ -1,0 +1,103 @@
+// bp_single.cuh -- node-parallel BP kernel for SMALL batches (decode! of one syndrome, a handful of columns).
+//
+// The persistent kernel (bp_kernel.cuh) maps one syndrome to one lane: a batch of 1 keeps 1 lane of 1 SM busy
+// for max_iters * (s + n) sequential node updates.  Here one CTA decodes one syndrome and its threads own
+// the nodes: thread t updates checks t, t+T, ... then variables t, t+T, ... of
+// decode!(::BeliefPropagationDecoder, syndrome)  (/root/reference/src/decoders/belief_propagation.jl:121-188).
+// Same arithmetic (bp_math.cuh: check_update<D>, var_update<D>, decide), same storage (one in-place message
+// array in check-major edge order, in shared memory), same incremental residual syndrome for the :180-184
+// early stop, so results are bit-identical to the persistent kernel and to the oracle.  Graph tables are in
+// the ORIGINAL node order (no degree sorting needed: nodes are not walked in lock step).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define BP_VARIANT 0
+#include "bp_math.cuh"
+#include "bp_single.h"
+
+namespace bp {
+
+template <int T>
+__global__ void __launch_bounds__(T, 1) bp_node_parallel_kernel(const SingleParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double *msg = reinterpret_cast<double *>(sm_raw);
+    uint32_t *syn = reinterpret_cast<uint32_t *>(sm_raw + p.off_syn);
+    uint32_t *resid = reinterpret_cast<uint32_t *>(sm_raw + p.off_resid);
+    uint32_t *dec = reinterpret_cast<uint32_t *>(sm_raw + p.off_dec);      // decisions, bit-packed like the output row
+    const int tid = threadIdx.x;
+    const double p0 = p.p0;
+    const bool regular_p0 = p.regular_p0 != 0;
+
+    for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+        for (int w = tid; w < p.SW; w += T) { const uint32_t v = p.syn_words[b * p.SW + w]; syn[w] = v; resid[w] = v; }
+        for (int w = tid; w < p.NW; w += T) dec[w] = 0u;                   // err .= 0 (reset!, :89)
+        __syncthreads();
+        bool conv = false;
+        int iter = 0;
+        while (iter < p.max_iters) {                                       // :134
+            const bool fresh = iter == 0;                                  // messages still hold the prior (:127-131)
+            // ---- check pass (:135-150)
+            for (int i = tid; i < p.s; i += T) {
+                const int rp = p.rowptr[i], deg = p.rowptr[i + 1] - rp;
+                const bool neg = (syn[i >> 5] >> (i & 31)) & 1u;
+#define BP_CASE(D)                                                                    \
+    {                                                                                 \
+        double m[D];                                                                  \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = fresh ? p0 : msg[rp + k]; \
+        check_update<D>(m, neg, 0.0);                                                 \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) msg[rp + k] = m[k];             \
+    }
+                BP_DEGREE_SWITCH(deg, BP_CASE, ;)
+#undef BP_CASE
+            }
+            __syncthreads();
+            // ---- variable pass, decision, residual syndrome (:152-184)
+            const bool wr = p.ratio != nullptr && (!p.ratio_last_only || iter + 1 >= p.max_iters);
+            for (int j = tid; j < p.n; j += T) {
+                const int cp = p.colptr[j], deg = p.colptr[j + 1] - cp;
+                double R = p0;
+#define BP_CASE(D)                                                                    \
+    {                                                                                 \
+        int sl[D];                                                                    \
+        double m[D];                                                                  \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) sl[k] = p.ve_slot[cp + k];      \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = msg[sl[k]];              \
+        R = var_update<D>(m, p0, regular_p0);                                         \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) msg[sl[k]] = m[k];              \
+    }
+                BP_DEGREE_SWITCH(deg, BP_CASE, ;)
+#undef BP_CASE
+                if (wr) p.ratio[b * p.n + j] = R;
+                const uint32_t bit = decide(R) ? 1u : 0u;                  // tie -> 1 (:164)
+                if (bit != ((dec[j >> 5] >> (j & 31)) & 1u)) {
+                    atomicXor(&dec[j >> 5], 1u << (j & 31));
+                    for (int e = cp; e < cp + deg; ++e) {
+                        const int c = p.ve_chk[e];
+                        atomicXor(&resid[c >> 5], 1u << (c & 31));
+                    }
+                }
+            }
+            __syncthreads();
+            bool nz = false;
+            for (int w = tid; w < p.SW; w += T) nz |= resid[w] != 0u;
+            conv = __syncthreads_or(nz) == 0;                              // H*err mod 2 == syndrome (:180-181)
+            ++iter;
+            if (p.early_stop && conv) break;                               // :182-184
+        }
+        for (int w = tid; w < p.NW; w += T) p.err_words[b * p.NW + w] = dec[w];
+        if (tid == 0) {
+            p.conv[b] = conv ? 1 : 0;
+            if (p.iters) p.iters[b] = iter;
+            if (p.counters) {
+                atomicAdd(&p.counters[0], 1ull);
+                atomicAdd(&p.counters[1], conv ? 1ull : 0ull);
+                atomicAdd(&p.counters[2], static_cast<unsigned long long>(iter));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace bp

@@ -20,6 +20,7 @@
 #define BP_WITH_SELFTEST 1
 #include "bp_launch.h"
 #include "bp_math.cuh"
+#include "bp_single.h"
 #include "formats.cuh"
 #include "osd.cuh"
 
@@ -115,6 +116,7 @@ struct ldpcb200 {
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
     double ms_scale = 0.875;     // min-sum normalisation factor (option "minsum_scale_permille")
+    int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
@@ -572,6 +574,25 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         }
         return 0;
     }
+    // ---- small batches: one CTA per syndrome, threads over the nodes (bp_single.cuh)
+    {
+        const int64_t limit = h->opt_small_batch < 0 ? d.sm_count : h->opt_small_batch;
+        const int off_syn = static_cast<int>((std::max<int64_t>(h->E, 1) * 8 + 15) / 16 * 16);
+        const int smem = off_syn + 2 * h->SW * 4 + h->NW * 4;
+        if (B <= limit && h->variant == LDPCB200_VARIANT_EXACT && !h->big && smem <= d.smem_optin && h->E * 8 < (1 << 30)) {
+            bp::SingleParams q{};
+            q.s = static_cast<int>(h->s); q.n = static_cast<int>(h->n); q.E = static_cast<int>(h->E);
+            q.SW = h->SW; q.NW = h->NW; q.max_iters = h->max_iters; q.early_stop = h->opt_early_stop;
+            q.regular_p0 = h->regular_p0; q.ratio_last_only = ratio_last_only ? 1 : 0; q.p0 = h->p0; q.B = B;
+            q.rowptr = d.d_rowptr; q.colptr = d.d_colptr; q.ve_slot = d.d_ve_slot; q.ve_chk = d.d_ve_chk;
+            q.syn_words = syn_words; q.err_words = err_words; q.conv = conv; q.iters = iters; q.ratio = ratio;
+            q.counters = counters;
+            q.off_syn = off_syn; q.off_resid = off_syn + h->SW * 4; q.off_dec = off_syn + 2 * h->SW * 4;
+            CU(bp::single_launch(static_cast<int>(B), smem, st, q));
+            h->launches++;
+            return 0;
+        }
+    }
     const long long nchunks = (B + 31) / 32;
     const int grid = static_cast<int>(std::min<long long>(nchunks, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
     const int thr = h->warps * 32;
@@ -929,6 +950,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
 {
     if (!h || !key) return fail(LDPCB200_EINVAL, "null handle or key");
     const std::string k(key);
+    if (k == "small_batch") { h->opt_small_batch = value; return 0; }
     if (k == "osd_profile") { h->opt_osd_profile = value ? 1 : 0; return 0; }
     if (k == "ratio_last_only") { h->opt_ratio_last_only = value ? 1 : 0; return 0; }
     if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration

@@ -96,7 +96,8 @@ def test_ragged_batches(pkg, oracle, codes, B, fam):
     H, _, mi = codes.config_matrix("C3")
     _, syn = oracle.sample(H, 0.06, 99, 1000, B)
     ref = oracle.batch_decode(H, 0.06, mi, syn)
-    assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam), ref)
+    # small_batch = 0: keep these small batches on the persistent (lane-per-syndrome) kernel
+    assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0), ref)
 
 
 @pytest.mark.parametrize("fam", [SMEM, GLOBAL])
@@ -106,12 +107,12 @@ def test_semantic_edge_cases(pkg, oracle, codes, fam):
     zero = np.zeros((s, 40), dtype=np.uint8)
     g = run_gpu(pkg, H, 0.01, 0, zero, family=fam)          # max_iters = 0
     assert not g["errors"].any() and not g["converged"].any() and (g["iters"] == 0).all()
-    g = run_gpu(pkg, H, 0.01, 5, zero, family=fam)          # zero syndrome: converged at iteration 1
+    g = run_gpu(pkg, H, 0.01, 5, zero, family=fam, small_batch=0)   # zero syndrome: converged at iteration 1
     assert not g["errors"].any() and g["converged"].all() and (g["iters"] == 1).all()
     for per in (0.5, 0.7, 0.999):                           # prior ratio >= 1, ties -> 1
         _, syn = oracle.sample(H, 0.3, 5, 0, 64)
         ref = oracle.batch_decode(H, per, 7, syn, want_ratio=True)
-        assert_same(run_gpu(pkg, H, per, 7, syn, family=fam, want_ratio=True), ref, want_ratio=True)
+        assert_same(run_gpu(pkg, H, per, 7, syn, family=fam, want_ratio=True, small_batch=0), ref, want_ratio=True)
     for mi in (1, 2, 3):                                    # non-converged outputs of iteration max_iters
         _, syn = oracle.sample(H, 0.1, 6, 0, 200)
         ref = oracle.batch_decode(H, 0.1, mi, syn, want_ratio=True)
@@ -148,7 +149,8 @@ def test_tiny_codes(pkg, oracle):
         syn = np.array([[(b >> i) & 1 for b in range(1 << s)] for i in range(s)], dtype=np.uint8)
         for fam in (SMEM, GLOBAL):
             ref = oracle.batch_decode(H, 0.1, 10, syn, want_ratio=True)
-            assert_same(run_gpu(pkg, H, 0.1, 10, syn, family=fam, want_ratio=True), ref, want_ratio=True)
+            assert_same(run_gpu(pkg, H, 0.1, 10, syn, family=fam, want_ratio=True, small_batch=0), ref, want_ratio=True)
+        assert_same(run_gpu(pkg, H, 0.1, 10, syn, want_ratio=True), ref, want_ratio=True)       # node-parallel kernel
 
 
 @pytest.mark.parametrize("fmt", ["u8", "i64", "bool"])
@@ -542,3 +544,48 @@ def test_bposd_large_batch_properties_and_host_device_agreement(pkg, oracle, cod
         assert np.array_equal(got, ref["errors"])
         assert np.array_equal(conv_h[first:first + cnt].astype(bool), ref["converged"])
     dec.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# node-parallel small-batch kernel (bp_single.cuh): the low-latency path of decode! and of batches up to one
+# CTA per SM; bit-identical to the oracle like the persistent kernel
+@pytest.mark.parametrize("name,per,B", [("C1", 0.01, 5), ("C1", 0.04, 64), ("C3", 0.06, 148), ("C3", 0.12, 33),
+                                        ("C2", 0.05, 100), ("C4", 0.03, 40), ("C4", 0.08, 7)])
+def test_small_batch_kernel_parity(pkg, oracle, codes, name, per, B):
+    H, _, mi = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 808, 0, B)
+    ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads(), want_ratio=True)
+    g = run_gpu(pkg, H, per, mi, syn, want_ratio=True, small_batch=1000)
+    assert_same(g, ref, want_ratio=True)
+    g0 = run_gpu(pkg, H, per, mi, syn, want_ratio=True, small_batch=0)        # persistent kernel, same bits
+    assert_same(g0, ref, want_ratio=True)
+
+
+def test_small_batch_kernel_edge_cases(pkg, oracle, codes):
+    H, _, _ = codes.config_matrix("C3")
+    s, n = H.shape
+    zero = np.zeros((s, 9), dtype=np.uint8)
+    g = run_gpu(pkg, H, 0.01, 5, zero)                       # zero syndrome: converged at iteration 1
+    assert not g["errors"].any() and g["converged"].all() and (g["iters"] == 1).all()
+    for per in (0.5, 0.7, 0.999):                            # prior ratio >= 1, ties -> 1
+        _, syn = oracle.sample(H, 0.3, 5, 0, 64)
+        ref = oracle.batch_decode(H, per, 7, syn, want_ratio=True)
+        assert_same(run_gpu(pkg, H, per, 7, syn, want_ratio=True), ref, want_ratio=True)
+    for mi in (1, 2, 3):                                     # non-converged outputs of iteration max_iters
+        _, syn = oracle.sample(H, 0.1, 6, 0, 100)
+        ref = oracle.batch_decode(H, 0.1, mi, syn, want_ratio=True)
+        assert_same(run_gpu(pkg, H, 0.1, mi, syn, want_ratio=True), ref, want_ratio=True)
+    # forced iterations (early_stop = 0) and irregular graphs with empty rows/columns
+    _, syn = oracle.sample(H, 0.05, 7, 0, 50)
+    g = run_gpu(pkg, H, 0.05, 6, syn, early_stop=0)
+    assert (g["iters"] == 6).all()
+    rng = np.random.default_rng(9)
+    Hd = (rng.random((30, 70)) < 0.08).astype(np.uint8)
+    Hd[3, :] = 0
+    Hd[:, 7] = 0
+    Hi = sp.csc_matrix(Hd)
+    e = (rng.random((70, 60)) < 0.05).astype(np.uint8)
+    syn = np.asarray((Hi @ e) % 2).astype(np.uint8)
+    syn[3, ::5] = 1
+    ref = oracle.batch_decode(Hi, 0.05, 15, syn, want_ratio=True)
+    assert_same(run_gpu(pkg, Hi, 0.05, 15, syn, want_ratio=True), ref, want_ratio=True)

@@ -62,10 +62,14 @@ if his:
                 sm = int(x[ix[col]])
             except ValueError:
                 sm = 0
-            lines.append((k, sm, x[ix["Source"]]))
+            try:
+                ex = int(x[ix["Instructions Executed"]])
+            except ValueError:
+                ex = 0
+            lines.append((k, sm, "%10d  %s" % (ex, x[ix["Source"]])))
         tots = sum(l[1] for l in lines) or 1
         with open(sys.argv[2], "w") as f:
-            f.write("# SASS listing with %s (total %d)\n" % (col, tots))
+            f.write("# SASS listing: index, %s, share, warp-instructions executed, instruction (total samples %d)\n" % (col, tots))
             for k, sm, src_ in lines:
                 f.write("%5d %7d %5.1f%%  %s\n" % (k, sm, 100.0 * sm / tots, src_))
         print("-" * 100)

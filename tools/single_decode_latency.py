@@ -18,3 +18,36 @@ gpu = (time.perf_counter() - t0) / 200
 t0 = time.perf_counter(); oracle.batch_decode(H, per, mi, syn, dense=True); dense = (time.perf_counter() - t0) / 200
 t0 = time.perf_counter(); oracle.batch_decode(H, per, mi, syn); edge = (time.perf_counter() - t0) / 200
 print("C1 single decode!: GPU (ctypes mirror, host vectors in/out) %.1f us; CPU restatement dense %.1f us, edge-indexed %.1f us" % (gpu * 1e6, dense * 1e6, edge * 1e6))
+
+# kernel-level view: forced 25 iterations (early stop off), device-resident, B = 1 and B = 100, both kernels
+import torch
+dev = torch.device("cuda:0")
+info = dec.info()
+SW, NW = info["syn_words"], info["err_words"]
+for B in (1, 100):
+    truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
+    errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    conv = torch.empty(B, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    dec.sample_device(B, 0, 2024, per, truth.data_ptr(), synw.data_ptr(), stream=st)
+    out = []
+    for early in (1, 0):
+        dec.set_option("early_stop", early)
+        for sb in (0, -1):
+            dec.set_option("small_batch", sb)
+            for _ in range(5):
+                dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), None, None, None, stream=st)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(50):
+                dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), None, None, None, stream=st)
+            b_.record(stream)
+            torch.cuda.synchronize()
+            out.append("%s/%s %.1f us" % ("early-stop" if early else "forced-25", "persistent" if sb == 0 else "node-parallel",
+                                          a.elapsed_time(b_) / 50 * 1e3))
+    print("C1 device-resident decode of %d syndrome(s): %s" % (B, "; ".join(out)))
+dec.close()
