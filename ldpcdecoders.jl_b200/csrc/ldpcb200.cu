@@ -70,6 +70,27 @@ struct DevBuf {
     T *as() const { return static_cast<T *>(p); }
 };
 
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        CU(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct DeviceCtx {
     int device = 0;
     int sm_count = 0;
@@ -92,6 +113,8 @@ struct DeviceCtx {
     } set[2];
     cudaEvent_t decode_done = nullptr;
     DevBuf counters, scratch, osd_stats;
+    DevBuf tiny;            // small-batch host calls: one device block ...
+    PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
 
 }  // namespace
@@ -379,7 +402,8 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats}) b->release();
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny}) b->release();
+    d.tiny_host.release();
     for (auto &S : d.set)
         for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
             b->release();
@@ -718,14 +742,102 @@ size_t fmt_bytes(int fmt, int64_t rows, int64_t ld, int64_t B, int RW)
 
 inline int grid_for(long long work, int sm) { return static_cast<int>(std::max<long long>(1, std::min<long long>((work + 255) / 256, static_cast<long long>(sm) * 16))); }
 
+// Small host batch (decode! and a handful of columns): everything goes through ONE device block and its pinned
+// mirror -- one host->device copy, the kernels, one device->host copy, one synchronisation -- instead of the
+// chunked double-buffered pipeline below, whose fixed cost (~10 API calls and 4 blocking copies) dominates here.
+int decode_host_tiny(ldpcb200 *h, DeviceCtx &d, int64_t B, const void *syndromes, int syn_fmt, int64_t syn_ld, void *errors,
+                     int err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *ratio, int64_t *counters_out)
+{
+    const int64_t s = h->s, n = h->n;
+    cudaStream_t st = d.set[0].stream;
+    auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t in_bytes = fmt_bytes(syn_fmt, s, syn_ld, B, h->SW), out_bytes = fmt_bytes(err_fmt, n, err_ld, B, h->NW);
+    const size_t synw_bytes = static_cast<size_t>(B) * h->SW * 4, errw_bytes = static_cast<size_t>(B) * h->NW * 4;
+    // device block:  [in_raw | syn_words | err_words]  then the part copied back: [out_raw | conv | iters | ratio | counters]
+    const size_t o_in = 0, o_synw = up16(in_bytes), o_errw = o_synw + up16(synw_bytes), o_out = o_errw + up16(errw_bytes);
+    const size_t o_conv = o_out + up16(out_bytes), o_iters = o_conv + up16(static_cast<size_t>(B));
+    const size_t o_ratio = o_iters + up16(static_cast<size_t>(B) * 4);
+    const size_t o_ctr = o_ratio + (ratio ? up16(static_cast<size_t>(B) * n * 8) : 0);
+    const size_t total = o_ctr + LDPCB200_NUM_COUNTERS * 8;
+    int rc;
+    if ((rc = d.tiny.reserve(total)) || (rc = d.tiny_host.reserve(total))) return rc;
+    unsigned char *D = d.tiny.as<unsigned char>(), *P = static_cast<unsigned char *>(d.tiny_host.p);
+    uint32_t *syn_words = reinterpret_cast<uint32_t *>(D + o_synw), *err_words = reinterpret_cast<uint32_t *>(D + o_errw);
+    // ---- in
+    const bool in_packed = syn_fmt == LDPCB200_FMT_PACKED32;
+    memcpy(P + o_in, syndromes, in_bytes);
+    CU(cudaMemcpyAsync(in_packed ? static_cast<void *>(syn_words) : static_cast<void *>(D + o_in), P + o_in, in_bytes,
+                       cudaMemcpyHostToDevice, st));
+    if (syn_fmt == LDPCB200_FMT_BITS)
+        bp::pack_bits<<<grid_for(B * h->SW, d.sm_count), 256, 0, st>>>(reinterpret_cast<uint32_t *>(D + o_in),
+                                                                       static_cast<long long>(in_bytes / 4), static_cast<int>(s), h->SW, B, syn_words);
+    else if (syn_fmt == LDPCB200_FMT_U8)
+        bp::pack_elems<uint8_t><<<grid_for(B * h->SW, d.sm_count), 256, 0, st>>>(D + o_in, syn_ld, static_cast<int>(s), h->SW, B, syn_words);
+    else if (syn_fmt == LDPCB200_FMT_I64)
+        bp::pack_elems<long long><<<grid_for(B * h->SW, d.sm_count), 256, 0, st>>>(reinterpret_cast<long long *>(D + o_in), syn_ld,
+                                                                                   static_cast<int>(s), h->SW, B, syn_words);
+    else if (!in_packed)
+        return fail(LDPCB200_EINVAL, "unsupported syndrome format %d", syn_fmt);
+    if (!in_packed) h->launches++;
+    // ---- decode
+    CU(cudaMemsetAsync(D + o_out, 0, total - o_out, st));
+    rc = decode_on_device(h, d, B, syn_words, err_words, D + o_conv, reinterpret_cast<int32_t *>(D + o_iters),
+                          ratio ? reinterpret_cast<double *>(D + o_ratio) : nullptr,
+                          reinterpret_cast<unsigned long long *>(D + o_ctr), st);
+    if (rc) return rc;
+    // ---- out
+    const int g = grid_for(B * h->NW, d.sm_count);
+    if (err_fmt == LDPCB200_FMT_PACKED32) {
+        CU(cudaMemcpyAsync(D + o_out, err_words, errw_bytes, cudaMemcpyDeviceToDevice, st));
+    } else if (err_fmt == LDPCB200_FMT_BITS) {
+        bp::unpack_bits<<<grid_for(static_cast<long long>(out_bytes / 4), d.sm_count), 256, 0, st>>>(
+            err_words, static_cast<int>(n), h->NW, B, reinterpret_cast<uint32_t *>(D + o_out), static_cast<long long>(out_bytes / 4));
+        h->launches++;
+    } else if (err_fmt == LDPCB200_FMT_U8) {
+        bp::unpack_elems<uint8_t><<<g, 256, 0, st>>>(err_words, static_cast<int>(n), h->NW, B, D + o_out, err_ld);
+        h->launches++;
+    } else if (err_fmt == LDPCB200_FMT_I64) {
+        bp::unpack_elems<long long><<<g, 256, 0, st>>>(err_words, static_cast<int>(n), h->NW, B, reinterpret_cast<long long *>(D + o_out), err_ld);
+        h->launches++;
+    } else if (err_fmt == LDPCB200_FMT_F64) {
+        bp::unpack_elems<double><<<g, 256, 0, st>>>(err_words, static_cast<int>(n), h->NW, B, reinterpret_cast<double *>(D + o_out), err_ld);
+        h->launches++;
+    } else {
+        return fail(LDPCB200_EINVAL, "unsupported error format %d", err_fmt);
+    }
+    CU(cudaMemcpyAsync(P + o_out, D + o_out, total - o_out, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const bool elems = err_fmt == LDPCB200_FMT_U8 || err_fmt == LDPCB200_FMT_I64 || err_fmt == LDPCB200_FMT_F64;
+    if (elems && err_ld != n) {          // strided destination: only the n rows of each column belong to the caller
+        const size_t esz = err_fmt == LDPCB200_FMT_U8 ? 1 : 8;
+        for (int64_t b = 0; b < B; ++b)
+            memcpy(static_cast<unsigned char *>(errors) + static_cast<size_t>(b) * err_ld * esz, P + o_out + static_cast<size_t>(b) * err_ld * esz,
+                   static_cast<size_t>(n) * esz);
+    } else {
+        memcpy(errors, P + o_out, out_bytes);
+    }
+    memcpy(converged, P + o_conv, static_cast<size_t>(B));
+    if (iters) memcpy(iters, P + o_iters, static_cast<size_t>(B) * 4);
+    if (ratio) memcpy(ratio, P + o_ratio, static_cast<size_t>(B) * n * 8);
+    unsigned long long hc[LDPCB200_NUM_COUNTERS];
+    memcpy(hc, P + o_ctr, sizeof(hc));
+    for (int k = 0; k < LDPCB200_NUM_COUNTERS; ++k) counters_out[k] = static_cast<int64_t>(hc[k]);
+    return 0;
+}
+
 // One device's share [b0, b0+Bd) of a host batch, processed in chunks.
 int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t Btot, const void *syndromes,
                       int syn_fmt, int64_t syn_ld, void *errors, int err_fmt, int64_t err_ld, uint8_t *converged,
                       int32_t *iters, double *ratio, int64_t *counters_out, bool osd = false, int64_t *osd_stats_out = nullptr)
 {
-    (void)Btot;
     CU(cudaSetDevice(d.device));
     const int64_t s = h->s, n = h->n;
+    {
+        const int64_t limit = h->opt_small_batch < 0 ? d.sm_count : h->opt_small_batch;
+        if (!osd && b0 == 0 && Bd == Btot && Bd <= limit && h->opt_chunk <= 0 &&
+            static_cast<double>(Bd) * (static_cast<double>(n) * 8.0 * (ratio ? 2 : 1) + static_cast<double>(s) * 8.0) < 64.0 * 1048576.0)
+            return decode_host_tiny(h, d, Bd, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, ratio, counters_out);
+    }
     // chunk size: bound the staging footprint (two sets are in flight)
     const double per_syn = static_cast<double>(fmt_bytes(syn_fmt, s, syn_ld, 2, h->SW) - fmt_bytes(syn_fmt, s, syn_ld, 1, h->SW)) +
                            static_cast<double>(fmt_bytes(err_fmt, n, err_ld, 2, h->NW) - fmt_bytes(err_fmt, n, err_ld, 1, h->NW)) +

@@ -589,3 +589,60 @@ def test_small_batch_kernel_edge_cases(pkg, oracle, codes):
     syn[3, ::5] = 1
     ref = oracle.batch_decode(Hi, 0.05, 15, syn, want_ratio=True)
     assert_same(run_gpu(pkg, Hi, 0.05, 15, syn, want_ratio=True), ref, want_ratio=True)
+
+
+@pytest.mark.parametrize("B", [1, 7, 64, 148])
+def test_small_batch_host_path_all_formats(pkg, oracle, codes, B):
+    """Small host batches go through one staging block each way (decode_host_tiny): every boundary format,
+    strided matrices, iteration counts, posterior ratios and counters."""
+    lib = pkg._lib
+    H, _, mi = codes.config_matrix("C2")
+    s, n = H.shape
+    _, syn = oracle.sample(H, 0.04, 21, 0, B)
+    ref = oracle.batch_decode(H, 0.04, mi, syn, want_ratio=True)
+    dec = pkg.BeliefPropagationDecoder(H, 0.04, mi)
+    conv = np.zeros(B, dtype=np.uint8)
+    iters = np.zeros(B, dtype=np.int32)
+    ratio = np.zeros((n, B), dtype=np.float64, order="F")
+    # element formats, leading dimensions larger than the row count (views into bigger Julia matrices)
+    for dt, fmt in ((np.uint8, lib.FMT_U8), (np.int64, lib.FMT_I64)):
+        big_in = np.full((s + 5, B), 3, dtype=dt, order="F")
+        big_in[:s] = syn
+        for odt, ofmt in ((np.uint8, lib.FMT_U8), (np.int64, lib.FMT_I64), (np.float64, lib.FMT_F64)):
+            big_out = np.full((n + 3, B), 9, dtype=odt, order="F")
+            ctr = dec.decode_raw(B, big_in, fmt, s + 5, big_out, ofmt, n + 3, conv, iters, ratio)
+            assert np.array_equal(big_out[:n].astype(np.uint8), ref["errors"]) and (big_out[n:] == 9).all()
+            assert np.array_equal(conv.astype(bool), ref["converged"]) and np.array_equal(iters, ref["iters"])
+            assert np.array_equal(ratio.view(np.uint64), ref["ratio"].view(np.uint64))
+            assert ctr[0] == B and ctr[1] == int(ref["converged"].sum()) and ctr[2] == int(ref["iters"].sum())
+    # BitMatrix stream and packed rows
+    bits_in = np.packbits(syn.T.reshape(-1), bitorder="little")
+    bits_in = np.concatenate([bits_in, np.zeros((-len(bits_in)) % 8, dtype=np.uint8)])
+    out = np.zeros(((B * n + 63) // 64) * 8, dtype=np.uint8)
+    dec.decode_raw(B, bits_in, lib.FMT_BITS, 0, out, lib.FMT_BITS, 0, conv)
+    assert np.array_equal(np.unpackbits(out, bitorder="little")[: B * n].reshape(B, n).T, ref["errors"])
+    SW, NW = (s + 31) // 32, (n + 31) // 32
+    pin = np.zeros((B, SW * 32), dtype=np.uint8)
+    pin[:, :s] = syn.T
+    pin = np.packbits(pin, axis=1, bitorder="little").view(np.uint32).copy()
+    pout = np.zeros((B, NW), dtype=np.uint32)
+    dec.decode_raw(B, pin, lib.FMT_PACKED32, 0, pout, lib.FMT_PACKED32, 0, conv)
+    assert np.array_equal(np.unpackbits(pout.view(np.uint8), axis=1, bitorder="little")[:, :n].T, ref["errors"])
+    # the same through the chunked pipeline (small_batch = 0)
+    dec.set_option("small_batch", 0)
+    out2 = np.zeros((n, B), dtype=np.uint8, order="F")
+    dec.decode_raw(B, np.asfortranarray(syn), lib.FMT_U8, s, out2, lib.FMT_U8, n, conv)
+    assert np.array_equal(out2, ref["errors"])
+    dec.close()
+    # max_iters = 0 and the min-sum variant (persistent kernel behind the same host path)
+    d0 = pkg.BeliefPropagationDecoder(H, 0.04, 0)
+    e0 = np.ones((n, B), dtype=np.uint8, order="F")
+    d0.decode_raw(B, np.asfortranarray(syn), lib.FMT_U8, s, e0, lib.FMT_U8, n, conv)
+    assert not e0.any() and not conv.any()
+    d0.close()
+    refm = oracle.batch_decode(H, 0.04, mi, syn, variant="minsum")
+    dm = pkg.BeliefPropagationDecoder(H, 0.04, mi, variant="minsum")
+    em = np.zeros((n, B), dtype=np.uint8, order="F")
+    dm.decode_raw(B, np.asfortranarray(syn), lib.FMT_U8, s, em, lib.FMT_U8, n, conv)
+    assert np.array_equal(em, refm["errors"]) and np.array_equal(conv.astype(bool), refm["converged"])
+    dm.close()
