@@ -646,3 +646,14 @@ def test_small_batch_host_path_all_formats(pkg, oracle, codes, B):
     dm.decode_raw(B, np.asfortranarray(syn), lib.FMT_U8, s, em, lib.FMT_U8, n, conv)
     assert np.array_equal(em, refm["errors"]) and np.array_equal(conv.astype(bool), refm["converged"])
     dm.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_bposd_in_library_sharding_over_two_devices(pkg, oracle, codes):
+    H, _, mi = codes.config_matrix("C3")
+    B = 5000
+    _, syn = oracle.sample(H, 0.08, 1234, 0, B)
+    ref = oracle.bposd_decode(H, 0.08, mi, syn, nthreads=oracle.num_threads())
+    g = run_gpu_bposd(pkg, H, 0.08, mi, syn, devices=[0, 1])
+    assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
+    assert g["stats"][0] == int((~ref["converged"]).sum()) and g["counters"][0] == B
