@@ -476,7 +476,9 @@ int pick_warps(int64_t s, int64_t n, int wmin, int wmax)
     for (int w = wmin; w <= wmax; ++w) {
         const double ec = s > 0 ? static_cast<double>(s) / (w * ((s + w - 1) / w)) : 1.0;
         const double ev = n > 0 ? static_cast<double>(n) / (w * ((n + w - 1) / w)) : 1.0;
-        const double score = 0.6 * ec + 0.4 * ev + 0.004 * w;
+        // equally even splits: more warps up to 8 (the 256-thread shape, <= 128 registers); the 384-thread shape
+        // is capped at 80 registers and spills per-iteration state, measured 2.7 % slower on C3 at the same evenness
+        const double score = 0.6 * ec + 0.4 * ev + 0.004 * std::min(w, 8) - 0.002 * std::max(0, w - 8);
         if (score > best) { best = score; best_w = w; }
     }
     return best_w;
