@@ -344,9 +344,11 @@ def main():
                         "peak = %d SMs x 64 FP64 lanes/clk x median SM clock under load (%.0f MHz); one FLOP = one FP64 lane-instruction" % (
                             FP64_SLOTS_PER_EDGE_ITER, info["sm_count"], clk_mhz),
                 "ncu": ({"launch": "2 000 000-syndrome launch of this workload under ncu --set full (not a bench value)",
-                         "smsp__issue_active_pct": 61.2, "sm__pipe_fp64_cycles_active_pct": 41.8,
-                         "fp64_share_of_issued_warp_instructions_pct": 34.6, "executed_fp64_slots_per_edge_iteration": 21,
-                         "dram_bytes_read": 66949120, "dram_bytes_write": 10175488,
+                         "smsp__issue_active_pct": 57.1, "sm__pipe_fp64_cycles_active_pct": 42.4,
+                         "fp64_share_of_issued_warp_instructions_pct": 37.4, "executed_fp64_slots_per_edge_iteration": 21,
+                         "dram_bytes_read": 64074240, "dram_bytes_write": 2648832,
+                         "previous_12_warp_shape": {"smsp__issue_active_pct": 61.2, "sm__pipe_fp64_cycles_active_pct": 41.8,
+                                                    "source": "profiles/r1_persistent_kernel_c3_mode0_12warps_ncu_full.txt"},
                          "source": "profiles/r1_persistent_kernel_c3_mode0_ncu_full.txt"}
                         if args.workload == "C3" and args.variant == "exact" else None),
                 "hbm_model": {"achieved_GBps": alg_bytes / step_s / 1e9, "peak_GBps": peaks["hbm_gbs"], "peak_source": peaks_src,
