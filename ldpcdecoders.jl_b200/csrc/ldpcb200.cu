@@ -849,8 +849,11 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     // resident slots (a smaller chunk leaves SMs idle); staging bounded by 256 MB per set, or what
     // two waves need (<= 2 GB)
     const double two_waves = 2.0 * h->slots * std::max(per_syn, 1.0);
-    const double budget = std::min(std::max(256.0 * 1048576.0, two_waves), 2048.0 * 1048576.0);
-    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>({(Bd + 3) / 4, 32768, 2 * static_cast<int64_t>(h->slots)});
+    // (the OSD pipeline keeps n posterior ratios per syndrome on the device: its chunks are bounded by 2 GB, and two
+    // chunks per call are enough to overlap the copies -- every chunk pays a BP tail and an OSD tail)
+    const double budget = osd ? 2048.0 * 1048576.0 : std::min(std::max(256.0 * 1048576.0, two_waves), 2048.0 * 1048576.0);
+    int64_t CH = h->opt_chunk > 0 ? h->opt_chunk
+                                  : std::max<int64_t>({(Bd + (osd ? 1 : 3)) / (osd ? 2 : 4), 32768, 2 * static_cast<int64_t>(h->slots)});
     CH = std::min<int64_t>(CH, static_cast<int64_t>(budget / std::max(per_syn, 1.0)));
     CH = std::max<int64_t>(32, (CH + 31) / 32 * 32);
     int rc;
