@@ -109,16 +109,14 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
         // bitonic sort of (key, idx) pairs
         for (int k = 2; k <= NP; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < NP; i += T) {
-                    const int x = i ^ j;
-                    if (x > i) {
-                        const unsigned long long ka = key[i], kb = key[x];
-                        const int ia = idx[i], ib = idx[x];
-                        const bool gt = ka > kb || (ka == kb && ia > ib);
-                        if (gt == ((i & k) == 0)) {
-                            key[i] = kb; key[x] = ka;
-                            idx[i] = ib; idx[x] = ia;
-                        }
+                for (int q = tid; q < NP / 2; q += T) {        // one compare-exchange per thread and trip, no idle lanes
+                    const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), x = i | j;
+                    const unsigned long long ka = key[i], kb = key[x];
+                    const int ia = idx[i], ib = idx[x];
+                    const bool gt = ka > kb || (ka == kb && ia > ib);
+                    if (gt == ((i & k) == 0)) {
+                        key[i] = kb; key[x] = ka;
+                        idx[i] = ib; idx[x] = ia;
                     }
                 }
                 __syncthreads();
