@@ -429,10 +429,15 @@ def main():
                           "converged_frac": float(c2[1]) / float(c2[0]), "syndrome_iterations_per_s": float(c2[2]) / secs2})
             d2.close()
             dec = dec_saved
-        dec.set_option("early_stop", 0)
+        # forced iterations: its own decoder, so that the library configures for that mode (early_stop = 0 before the
+        # first decode selects the 12-warp shape; the early-stop runs use 8 warps)
+        d2 = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], early_stop=0, **opts)
+        dec_saved = dec
+        dec = d2
         sample(per)
         secs2, c2, _ = timed_run(2, 1)
-        dec.set_option("early_stop", 1)
+        d2.close()
+        dec = dec_saved
         sweep.append({"per": per, "forced_iters": mi, "value": float(c2[0]) / secs2, "mean_iters": float(c2[2]) / float(c2[0]),
                       "syndrome_iterations_per_s": float(c2[2]) / secs2,
                       "fp64_frac": float(c2[2]) / 2 / world * E * FP64_SLOTS_PER_EDGE_ITER / (secs2 / 2) / 1e12 /
