@@ -1,10 +1,10 @@
-// the node-parallel small-batch kernel (exact variant) in its own translation unit
-#define BP_VARIANT 0
+// the node-parallel small-batch kernel (min-sum variant) in its own translation unit
+#define BP_VARIANT 1
 #include "bp_single.cuh"
 
 namespace bp {
 
-cudaError_t single_launch_0(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p)
+cudaError_t single_launch_1(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p)
 {
     auto k = bp_node_parallel_kernel<kSingleThreads>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

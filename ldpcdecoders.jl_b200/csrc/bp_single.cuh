@@ -12,11 +12,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef BP_VARIANT
 #define BP_VARIANT 0
+#endif
 #include "bp_math.cuh"
 #include "bp_single.h"
 
 namespace bp {
+inline namespace BP_VNS {
 
 template <int T>
 __global__ void __launch_bounds__(T, 1) bp_node_parallel_kernel(const SingleParams p)
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(T, 1) bp_node_parallel_kernel(const SinglePara
     {                                                                                 \
         double m[D];                                                                  \
         _Pragma("unroll") for (int k = 0; k < D; ++k) m[k] = fresh ? p0 : msg[rp + k]; \
-        check_update<D>(m, neg, 0.0);                                                 \
+        check_update<D>(m, neg, p.check_aux);                                         \
         _Pragma("unroll") for (int k = 0; k < D; ++k) msg[rp + k] = m[k];             \
     }
                 BP_DEGREE_SWITCH(deg, BP_CASE, ;)
@@ -100,4 +103,5 @@ __global__ void __launch_bounds__(T, 1) bp_node_parallel_kernel(const SinglePara
     }
 }
 
+}  // inline namespace BP_VNS
 }  // namespace bp

@@ -7,7 +7,8 @@ namespace bp {
 
 struct SingleParams {
     int s, n, E, SW, NW, max_iters, early_stop, regular_p0, ratio_last_only;
-    double p0;
+    double p0;         // prior ratio p/(1-p); min-sum variant: prior log-likelihood ratio
+    double check_aux;  // min-sum variant: normalisation factor
     long long B;
     const int *rowptr, *colptr, *ve_slot, *ve_chk;
     const uint32_t *syn_words;
@@ -20,6 +21,7 @@ struct SingleParams {
 };
 
 constexpr int kSingleThreads = 512;
-cudaError_t single_launch(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);
+cudaError_t single_launch_0(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);   // exact variant
+cudaError_t single_launch_1(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);   // min-sum variant
 
 }  // namespace bp

@@ -607,16 +607,17 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         const int64_t limit = h->opt_small_batch < 0 ? d.sm_count : h->opt_small_batch;
         const int off_syn = static_cast<int>((std::max<int64_t>(h->E, 1) * 8 + 15) / 16 * 16);
         const int smem = off_syn + 2 * h->SW * 4 + h->NW * 4;
-        if (B <= limit && h->variant == LDPCB200_VARIANT_EXACT && !h->big && smem <= d.smem_optin && h->E * 8 < (1 << 30)) {
+        if (B <= limit && !h->big && smem <= d.smem_optin && h->E * 8 < (1 << 30)) {
             bp::SingleParams q{};
             q.s = static_cast<int>(h->s); q.n = static_cast<int>(h->n); q.E = static_cast<int>(h->E);
             q.SW = h->SW; q.NW = h->NW; q.max_iters = h->max_iters; q.early_stop = h->opt_early_stop;
-            q.regular_p0 = h->regular_p0; q.ratio_last_only = ratio_last_only ? 1 : 0; q.p0 = h->p0; q.B = B;
+            q.regular_p0 = h->regular_p0; q.ratio_last_only = ratio_last_only ? 1 : 0; q.p0 = h->p0; q.check_aux = h->ms_scale; q.B = B;
             q.rowptr = d.d_rowptr; q.colptr = d.d_colptr; q.ve_slot = d.d_ve_slot; q.ve_chk = d.d_ve_chk;
             q.syn_words = syn_words; q.err_words = err_words; q.conv = conv; q.iters = iters; q.ratio = ratio;
             q.counters = counters;
             q.off_syn = off_syn; q.off_resid = off_syn + h->SW * 4; q.off_dec = off_syn + 2 * h->SW * 4;
-            CU(bp::single_launch(static_cast<int>(B), smem, st, q));
+            CU(h->variant == LDPCB200_VARIANT_MINSUM ? bp::single_launch_1(static_cast<int>(B), smem, st, q)
+                                                     : bp::single_launch_0(static_cast<int>(B), smem, st, q));
             h->launches++;
             return 0;
         }

@@ -657,3 +657,16 @@ def test_bposd_in_library_sharding_over_two_devices(pkg, oracle, codes):
     g = run_gpu_bposd(pkg, H, 0.08, mi, syn, devices=[0, 1])
     assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
     assert g["stats"][0] == int((~ref["converged"]).sum()) and g["counters"][0] == B
+
+
+@pytest.mark.parametrize("name,per,B", [("C3", 0.05, 60), ("C4", 0.04, 20), ("C1", 0.04, 9), ("C2", 0.03, 148)])
+def test_minsum_small_batch_kernel(pkg, oracle, codes, name, per, B):
+    """The node-parallel kernel of the min-sum variant against its CPU definition, and against the persistent kernel."""
+    H, _, mi = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 606, 0, B)
+    ref = oracle.batch_decode(H, per, mi, syn, variant="minsum", want_ratio=True)
+    for sb in (-1, 0):
+        g = run_gpu_variant(pkg, H, per, mi, syn, "minsum", small_batch=sb)
+        assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
+        assert np.array_equal(g["iters"], ref["iters"])
+        assert np.array_equal(g["ratio"].view(np.uint64), ref["ratio"].view(np.uint64))
