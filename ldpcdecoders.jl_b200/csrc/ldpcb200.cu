@@ -679,7 +679,7 @@ int osd_layout(const ldpcb200 *h, bp::OsdParams &p)
     off = (off + 15) / 16 * 16;
     p.off_key = static_cast<int>(off); off += static_cast<long long>(np) * 8;
     p.off_idx = static_cast<int>(off); off += static_cast<long long>(np) * 4;
-    p.off_piv = static_cast<int>(off); off += static_cast<long long>(std::max(m, 1)) * 4 * 4;   // piv, prow, pcol, list
+    p.off_piv = static_cast<int>(off); off += static_cast<long long>(std::max(m, 1)) * 4 * 5;   // piv, prow, pcol, list, rowat
     p.off_red = static_cast<int>(off); off += (16 + 192 + p.NWr / 4 + 1) * 4;
     return off > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(off);
 }

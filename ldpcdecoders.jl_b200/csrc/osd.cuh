@@ -5,12 +5,13 @@
 //   * order the columns by max(r, 1-r) descending, r = 1/R the posterior ratio P0/P1, stable (:53-55);
 //   * eliminate over GF(2) in that order until the remaining target is zero (:81-107), solve (:110-121),
 //     un-permute (:60).
-// What that computes is independent of the pivot-row choices: with S the first linearly independent columns
-// (in sorted order) up to the point where the residual syndrome lies in their span, the result is bp_err on
-// the columns outside S and bp_err xor d on S, d the unique solution of H_S d = syndrome xor H bp_err.  The
-// kernel computes exactly that with an elimination that never swaps rows (a row becomes "used" instead) and
-// a back substitution over the pivots; tests compare it bit for bit with the literal restatement in
-// oracle/bp_oracle.c.
+// For a syndrome in the column space of H that is: with S the first linearly independent columns (in sorted
+// order) up to the point where the residual syndrome lies in their span, bp_err on the columns outside S and
+// bp_err xor d on S, d the unique solution of H_S d = syndrome xor H bp_err -- whatever rows are taken as pivot
+// rows.  For a syndrome OUTSIDE the column space the outcome depends on which equations become pivot rows, so
+// the kernel takes the reference's: the first hit row in its physically swapped row order, which is tracked as
+// a position per row (the rows themselves never move; a row becomes "used" instead).  Back substitution over
+// the pivots as in the reference; tests compare bit for bit with the literal restatement in oracle/bp_oracle.c.
 // Converged syndromes are returned unchanged by the reference (:72-74) and are skipped here.
 //
 // One CTA per syndrome (work queue over the unconverged list).  Shared memory holds the whole augmented
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
     int *piv = reinterpret_cast<int *>(osd_smem + p.off_piv);          // [m] pivot number of a row, or -1
     int *prow = piv + p.m, *pcol = piv + 2 * p.m;                      // [m] row / sorted column of the q-th pivot
     int *list = piv + 3 * p.m;                                         // [m] rows to eliminate in the current step
+    int *rowat = piv + 4 * p.m;                                        // [m] row standing at a position of the reference's
+                                                                       //     (physically swapped) row order
     int *ctl = reinterpret_cast<int *>(osd_smem + p.off_red);          // [16] block-wide control words (see below)
     uint32_t *invtab = reinterpret_cast<uint32_t *>(ctl) + 16 + 192;   // [NWr/4 + 1] 2^32 / ng rounded up
     int *wcnts = ctl + 16;                                             // [2][96] per-warp hit counts / candidates / later bits
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
             idx[j] = j;
         }
         for (int i = tid; i < m * (NWr / 4); i += T) reinterpret_cast<uint4 *>(Hs)[i] = make_uint4(0, 0, 0, 0);
-        for (int r = tid; r < m; r += T) piv[r] = -1;
+        for (int r = tid; r < m; r += T) { piv[r] = -1; rowat[r] = r; }
         if (tid == 0) { ctl[2] = 0; ctl[12] = -1; }   // target count / solve round 0
         __syncthreads();
         // bitonic sort of (key, idx) pairs
@@ -148,6 +151,9 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
         // over all threads.
         // ctl[2]: number of unused rows whose target bit is set.
         uint32_t umask = 0;
+        int posr[RPT];                                    // position of the thread's rows in the reference's row order
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) posr[k] = tid + k * T;
         {
             int mine_t = 0;
             for (int r = tid, k = 0; r < m; r += T, ++k) {
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
                 later |= w;
                 hbs[k] = __ballot_sync(0xffffffffu, hit);
                 total += __popc(hbs[k]);
-                if (hit) cand = min(cand, r);
+                if (hit) cand = min(cand, (posr[k] << 12) | r);
             }
             cand = __reduce_min_sync(0xffffffffu, cand);
             later = __reduce_or_sync(0xffffffffu, later & ~(bj | (bj - 1u)));
@@ -181,11 +187,11 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
             // every warp redoes the small cross-warp reduction: pivot row, list offsets (prefix over the counts)
             int c = 0, mn = 0x7fffffff;
             if (lane < T / 32) { c = wb[lane]; mn = wb[32 + lane]; }
-            const int pr = __reduce_min_sync(0xffffffffu, mn);
+            const int best = __reduce_min_sync(0xffffffffu, mn);
             if (prof) { const long long t = clock64(); c_scan += t - t0; t0 = t; }
             if (ctl[2] == 0) break;                  // :82  remaining target is all zero
             ++steps;
-            if (pr == 0x7fffffff) {                  // :87  no pivot in this column; nothing changes until the next
+            if (best == 0x7fffffff) {                  // :87  no pivot in this column; nothing changes until the next
                 uint32_t lw = lane < T / 32 ? static_cast<uint32_t>(wb[64 + lane]) : 0u;   // column some unused row has
                 lw = __reduce_or_sync(0xffffffffu, lw);
                 const int nj = min(lw ? (wj << 5) + __ffs(static_cast<int>(lw)) - 1 : ((wj + 1) << 5), n);
@@ -200,11 +206,19 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
                 if ((hbs[k] >> lane) & 1u) list[base + __popc(hbs[k] & ((1u << lane) - 1u))] = tid + k * T;
                 base += __popc(hbs[k]);
             }
+            // pivot row = the hit row standing first in the reference's row order (:88 findfirst); the reference then swaps
+            // it with the row at position npiv (:94-98): that row, still unused, takes over the pivot row's old position
+            const int pr = best & 4095, kpos = best >> 12;
+            const int ri = rowat[npiv];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (tid + k * T == ri) posr[k] = kpos;
             const uint32_t ptgt = Hs[pr * NWr + augw] & augm;
             if (tid == 0) { prow[npiv] = pr; pcol[npiv] = j; }
             if ((pr % T) == tid) { umask &= ~(1u << (pr / T)); piv[pr] = npiv; }
-            ++npiv;
             __syncthreads();
+            if (tid == 0) rowat[kpos] = ri;          // (every thread has read rowat[npiv] before the barrier)
+            ++npiv;
             const int g0 = wj >> 2, ng = (NWr >> 2) - g0;
             const uint32_t inv = invtab[ng];         // q / ng by multiplication
             const uint4 *prow4 = reinterpret_cast<const uint4 *>(Hs + pr * NWr) + g0;

@@ -670,3 +670,22 @@ def test_minsum_small_batch_kernel(pkg, oracle, codes, name, per, B):
         assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
         assert np.array_equal(g["iters"], ref["iters"])
         assert np.array_equal(g["ratio"].view(np.uint64), ref["ratio"].view(np.uint64))
+
+
+def test_bposd_syndromes_outside_the_column_space(pkg, oracle, codes):
+    """Rank-deficient H and arbitrary syndromes: the elimination runs out of columns and which equations were made
+    pivot rows decides the output, so the kernel has to follow the reference's (swapped) row order.  Found by
+    tools/fuzz_parity.py; all posteriors tie at per = 0.5."""
+    for (n, wr, wc, per, mi) in ((120, 6, 3, 0.5, 7), (100, 10, 5, 0.5, 7), (200, 8, 4, 0.1, 3), (96, 4, 3, 0.02, 5)):
+        H = codes.gallager(n, wr, wc, seed=n + wr)
+        s = H.shape[0]
+        rng = np.random.default_rng(n)
+        syn = (rng.random((s, 300)) < 0.5).astype(np.uint8)
+        ref = oracle.bposd_decode(H, per, mi, syn, nthreads=oracle.num_threads())
+        Hd = np.asarray(sp.csc_matrix(H).todense()).astype(np.int64)
+        ok = ((Hd @ ref["errors"].astype(np.int64)) % 2 == syn).all(axis=0)
+        assert 0 < ok.sum() < 300 or not ok.any()                      # most syndromes cannot be satisfied
+        g = run_gpu_bposd(pkg, H, per, mi, syn)
+        bad = np.nonzero((g["errors"] != ref["errors"]).any(axis=0))[0]
+        assert bad.size == 0, (n, wr, wc, per, mi, bad[:10])
+        assert np.array_equal(g["converged"], ref["converged"]) and g["stats"][1] == int(ref["pivots"].sum())
