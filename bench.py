@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--family", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1)
+    ap.add_argument("--lean", type=int, default=-1, help="family SMEM: 1 = round-2 kernel (default), 0 = general persistent kernel")
     ap.add_argument("--variant", default="exact", choices=["exact", "minsum"],
                     help="exact = reference-parity sum-product (headline); minsum = normalised min-sum (no reference equivalent)")
     args = ap.parse_args()
@@ -249,6 +250,8 @@ def main():
         opts["warps"] = args.warps
     if args.prefetch >= 0:
         opts["prefetch"] = args.prefetch
+    if args.lean >= 0:
+        opts["lean"] = args.lean
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant=args.variant, **opts)
     info = dec.info()
     SW, NW = info["syn_words"], info["err_words"]
@@ -367,7 +370,7 @@ def main():
             "syndrome_iterations_per_s": float(c[2]) / secs,
             "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
             "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "smem_bytes", "slots",
-                                            "message_bytes", "prefetch_distance")}}
+                                            "message_bytes", "prefetch_distance", "kernel_rev")}}
 
     # ---- end to end through the host-buffer C-ABI call (Julia BitMatrix in / out), pinned memory
     if not args.no_e2e:

@@ -70,6 +70,8 @@ typedef struct {
     int64_t message_bytes;      /* device bytes of the message store per device (family GLOBAL) */
     int32_t kernel_mode;        /* 0: all in shared memory, 1: messages in HBM/L2, 2: messages + state + tables in HBM/L2 */
     int32_t prefetch_distance;  /* cp.async ring depth of modes 1/2 (0 = messages read directly) */
+    int32_t kernel_rev;         /* 2: round-2 shared-memory kernel (bp_smem.cuh), 1: the general persistent kernel (bp_kernel.cuh) */
+    int32_t counters_via_nccl;  /* 1: the per-device counters of a multi-device handle are summed with ncclAllReduce */
 } ldpcb200_info_t;
 
 /* counters[] layout of the decode calls (summed over all devices of the handle) */
@@ -103,7 +105,8 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
 
 /* Tunables, set before the first decode (all optional):
  *   "family" (LDPCB200_FAMILY_*), "warps" (warps per CTA), "prefetch" (cp.async prefetch distance of the
- *   HBM modes, 0..3),
+ *   HBM modes, 0..3), "lean" (family SMEM: 1 = round-2 kernel where the code fits its envelope (default),
+ *   0 = always the general persistent kernel),
  *   "minsum_scale_permille" (min-sum variant: normalisation factor x 1000, default 875),
  *   "early_stop" (1 = reference semantics, default; 0 = always run max_iters -- benchmarking only,
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk),

@@ -34,7 +34,8 @@ class Info(ctypes.Structure):
                 ("ctas_per_sm", ctypes.c_int32), ("threads_per_cta", ctypes.c_int32),
                 ("smem_bytes", ctypes.c_int32), ("slots", ctypes.c_int32),
                 ("syn_words", ctypes.c_int32), ("err_words", ctypes.c_int32),
-                ("message_bytes", ctypes.c_int64), ("kernel_mode", ctypes.c_int32), ("prefetch_distance", ctypes.c_int32)]
+                ("message_bytes", ctypes.c_int64), ("kernel_mode", ctypes.c_int32), ("prefetch_distance", ctypes.c_int32),
+                ("kernel_rev", ctypes.c_int32), ("counters_via_nccl", ctypes.c_int32)]
 
 
 class LibraryError(RuntimeError):

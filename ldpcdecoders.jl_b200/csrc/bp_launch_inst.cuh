@@ -32,16 +32,26 @@ cudaError_t BP_NAME(kernel_attrs_, BP_INST_MODE, BP_INST_BIG)(int shape, int sme
     return cudaErrorInvalidConfiguration;
 }
 
+// The dynamic-shared-memory limit is an attribute of the kernel instantiation on the current device, not of a
+// decoder handle: two live handles that share an instantiation but need different sizes would otherwise lower
+// each other's limit.  It is therefore (re)set before every launch (a host-side call of about a microsecond).
+template <int MAXT, int MINB>
+static void launch_one(int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p)
+{
+    auto k = bp_persistent_kernel<BP_INST_MODE, BP_INST_BIG != 0, MAXT, MINB>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return;   // surfaces through cudaGetLastError
+    k<<<grid, threads, smem_bytes, st>>>(p);
+}
+
 void BP_NAME(kernel_launch_, BP_INST_MODE, BP_INST_BIG)(int shape, int grid, int threads, int smem_bytes, cudaStream_t st,
                                                         const KernelParams &p)
 {
-    constexpr bool kBig = BP_INST_BIG != 0;
-    if (shape == kShape256x2) bp_persistent_kernel<BP_INST_MODE, kBig, 256, 2><<<grid, threads, smem_bytes, st>>>(p);
+    if (shape == kShape256x2) launch_one<256, 2>(grid, threads, smem_bytes, st, p);
 #if !BP_INST_BIG
-    if (shape == kShape384x2) bp_persistent_kernel<BP_INST_MODE, kBig, 384, 2><<<grid, threads, smem_bytes, st>>>(p);
+    if (shape == kShape384x2) launch_one<384, 2>(grid, threads, smem_bytes, st, p);
 #endif
 #if BP_INST_MODE == 0
-    if (shape == kShape512x1) bp_persistent_kernel<BP_INST_MODE, kBig, 512, 1><<<grid, threads, smem_bytes, st>>>(p);
+    if (shape == kShape512x1) launch_one<512, 1>(grid, threads, smem_bytes, st, p);
 #endif
 }
 

@@ -1,0 +1,260 @@
+// bp_smem.cuh -- the shared-memory-resident persistent BP kernel (family SMEM, round 2).
+//
+// Same mapping, arithmetic and results as bp_persistent_kernel<0, ...> (bp_kernel.cuh): CTA = 32
+// syndrome lanes x W warps, messages of 32 syndromes resident in shared memory for all iterations,
+// decode!/batchdecode! of /root/reference/src/decoders/belief_propagation.jl:121-188,220-231.
+// What differs is everything AROUND the node updates, which ncu showed to be a third of all issued
+// instructions of the round-1 kernel (profiles/r1_persistent_kernel_c3_mode0_ncu_full.txt):
+//   * two block barriers per iteration instead of three: an entering syndrome is read from its staging slot
+//     during its first check pass (per-lane syndrome row address), so the copy into the lane's own rows
+//     needs no barrier of its own;
+//   * the syndrome re-check (:180-184) is `residual == 0`, the residual s xor H*e being updated by
+//     NON-returning shared-memory atomics of the flipped variables; no per-lane count of unsatisfied
+//     checks, no returning atomics, no count exchange.  The residual of a lane is double-buffered per lane
+//     (an entering syndrome takes the other buffer) so that a warp still testing the leaving syndrome never
+//     sees the entering one;
+//   * 32-bit queue arithmetic (one launch handles fewer than 2^31 syndromes; the host splits larger batches),
+//     32-bit decision fields when a warp owns at most 32 variables;
+//   * degree segments only (the degree switch runs once per segment), no per-node paths, no decision fields
+//     in memory, no local-memory degrees: codes outside that envelope stay on the round-1 kernel.
+#pragma once
+#include <type_traits>
+
+#include "bp_kernel.cuh"
+
+namespace bp {
+inline namespace BP_VNS {
+
+template <int MAXT, int MINB, bool EB64>
+__global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_constant__ KernelParams p)
+{
+    using ebits_t = typename std::conditional<EB64, unsigned long long, uint32_t>::type;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t ml = sbase + lane * 8;                         // this lane's message column
+    const uint32_t syn_own = sbase + p.off_syn + lane * 4;        // this lane's syndrome words, [word][32] layout
+    const uint32_t res0 = sbase + p.off_resid + lane * 4;         // residual buffers 0 / 1 of this lane
+    const uint32_t res_sum = 2 * res0 + p.SW * 128;               // res0 + res1
+    const uint32_t stage_a = sbase + p.off_stage;                 // [2][SW][32] staged syndromes of the queue window
+    const uint32_t colptr_a = sbase + p.off_tables + p.off_colptr;
+    const uint32_t ve_a = sbase + p.off_tables + p.off_ve;        // u32 byte offset of each edge's slot row
+    const uint32_t vflip_a = sbase + p.off_tables + p.off_vflip;  // u16 residual word offset | bit of each edge's check
+    const uint32_t corig_a = sbase + p.off_tables + p.off_corig;
+    const uint32_t vorig_a = sbase + p.off_tables + p.off_vorig;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
+
+    auto vorig_at = [&](int j) -> int { return p.perm_v ? static_cast<int>(lds_u16(vorig_a + 2 * j)) : j; };
+
+    if (threadIdx.x == 0) tma_load_tables(smem + p.off_tables, p.tables, static_cast<uint32_t>(p.tables_bytes), mbar);
+
+    // This CTA's queue: 32-syndrome chunks c, c+G, c+2G, ... of the batch (B < 2^31 - 32*G, host-checked).
+    const int G = gridDim.x, c = blockIdx.x;
+    const int Bn = static_cast<int>(p.B);
+    const int nchunks = (Bn + 31) >> 5;
+    const int Q = (c < nchunks) ? (((nchunks - c + G - 1) / G) << 5) : 0;
+    auto sid_of = [&](int q) -> int {
+        const int sid = (((q >> 5) * G + c) << 5) + (q & 31);
+        return (q < Q && sid < Bn) ? sid : -1;
+    };
+    // wS moves staged syndromes into the lanes' own rows, wP prefetches the next queue window,
+    // wO writes converged flags / iteration counts and keeps the counters.
+    const int wS = 0, wP = (W > 1) ? 1 : 0, wO = (W > 2) ? 2 : 0;
+    auto prefetch = [&](int q_head, int buf) {            // stage[buf][w][r] <- syndrome words of entry q_head + r
+        const int sid = sid_of(q_head + lane);
+        if (sid >= 0) {
+            const uint32_t *src = p.syn_words + static_cast<size_t>(sid) * p.SW;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + p.off_stage) + buf * p.SW * 32 + lane;
+            for (int w = 0; w < p.SW; ++w) cp_async4(dst + w * 32, src + w);
+        }
+    };
+
+    int q_head = 0, sbuf = 0;
+    int sid = -1, iter = 0;
+    bool active = false, fresh = false;
+    uint32_t syn_a = syn_own;                             // where this lane's syndrome is read from in the check pass
+    uint32_t res_a = res0;                                // this lane's live residual buffer
+    ebits_t ebits = 0;                                    // decisions of the variables this warp owns (bit i <-> j = warp + i*W)
+    unsigned long long n_done = 0, n_conv = 0, n_iters = 0;   // warp wO only
+
+    if (warp == wP) { prefetch(0, 0); cp_async_wait_all(); }
+    __syncthreads();
+    mbar_wait(mbar, 0);                                   // tables have landed
+
+    // Lanes in `mask` take the next queue entries (identically in every warp: the lane state is replicated).
+    auto refill = [&](uint32_t mask) {
+        if ((mask >> lane) & 1u) {
+            const int rank = __popc(mask & lt_mask);
+            sid = sid_of(q_head + rank);
+            active = sid >= 0;
+            fresh = active;
+            iter = 0;
+            ebits = 0;                                    // err .= 0 (reset!, :89)
+            res_a = res_sum - res_a;                      // the other residual buffer
+            if (active) {
+                syn_a = stage_a + sbuf * (p.SW * 128) + rank * 4;
+                if (warp == wS)
+                    for (int w = 0; w < p.SW; ++w) {
+                        const uint32_t v = lds_u32(syn_a + w * 128);
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(syn_own + w * 128), "r"(v) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(res_a + w * 128), "r"(v) : "memory");
+                    }
+            }
+        }
+        q_head += __popc(mask);
+        sbuf ^= 1;
+        if (warp == wP) prefetch(q_head, sbuf);           // lands before the barrier that precedes the next refill
+    };
+
+    refill(0xffffffffu);
+    uint32_t any_active = __ballot_sync(0xffffffffu, active);
+
+    const double p0 = p.p0;
+    const double caux = p.check_aux;
+    const bool regular_p0 = p.regular_p0;
+    while (any_active != 0u) {
+        // ------------------------------------------------------------------ check pass (:135-150)
+        if (active) {
+            int i = warp;
+            for (int g = 0; g < p.seg.ncseg; ++g) {
+                const int deg = p.seg.cdeg[g], first = p.seg.cfirst[g], end = p.seg.cend[g], sb = p.seg.cslot[g];
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        uint32_t a = ml + (sb + (i - first) * D) * 256;                                          \
+        if (p.perm_c) {                                                                          \
+            for (; i < end; i += W, a += W * (D * 256)) {                                        \
+                const int io = static_cast<int>(lds_u16(corig_a + 2 * i));                       \
+                check_node<D>(a, (lds_u32(syn_a + (io >> 5) * 128) >> (io & 31)) & 1u, fresh, p0, caux); \
+            }                                                                                    \
+        } else {                                                                                 \
+            for (; i < end; i += W, a += W * (D * 256))                                          \
+                check_node<D>(a, (lds_u32(syn_a + (i >> 5) * 128) >> (i & 31)) & 1u, fresh, p0, caux); \
+        }                                                                                        \
+    }
+                BP_DEGREE_SWITCH(deg, BP_CASE, ;)
+#undef BP_CASE
+                if (deg == 0 && i < end) i += ((end - i + W - 1) / W) * W;   // isolated checks: nothing to send
+            }
+        }
+        fresh = false;
+        syn_a = syn_own;                                   // (wS copied the staged syndrome into the lane's own rows at refill time)
+        __syncthreads();
+        // --------------------------------------------------------------- variable pass (:152-178)
+        if (active) {
+            ebits_t newbits = 0;
+            const bool wr = p.ratio != nullptr && (!p.ratio_last_only || iter + 1 >= p.max_iters);
+            int j = warp, i = 0;
+            for (int g = 0; g < p.seg.nvseg; ++g) {
+                const int deg = p.seg.vdeg[g], first = p.seg.vfirst[g], end = p.seg.vend[g], eb = p.seg.vedge[g];
+                if (deg == 0) {                                           // isolated variables: prior only
+                    for (; j < end; j += W, ++i) {
+                        if (wr) p.ratio[static_cast<size_t>(sid) * p.n + vorig_at(j)] = p0;
+                        newbits |= static_cast<ebits_t>(decide(p0) ? 1u : 0u) << i;
+                    }
+                    continue;
+                }
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        uint32_t vea = ve_a + 4 * (eb + (j - first) * D);                                        \
+        const int step = W * D * 4;                                                              \
+        if constexpr (D <= 4) {                                                                  \
+            for (; j + W < end; j += 2 * W, i += 2, vea += 2 * step) {                           \
+                uint32_t va[D], vb[D];                                                           \
+                double ma[D], mb[D];                                                             \
+                load_offsets<D>(va, vea);                                                        \
+                load_offsets<D>(vb, vea + step);                                                 \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) ma[k] = ld_msg(ml + va[k]);        \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) mb[k] = ld_msg(ml + vb[k]);        \
+                const double Ra = var_update<D>(ma, p0, regular_p0);                             \
+                const double Rb = var_update<D>(mb, p0, regular_p0);                             \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + va[k], ma[k]);         \
+                _Pragma("unroll") for (int k = 0; k < D; ++k) st_msg(ml + vb[k], mb[k]);         \
+                if (wr) {                                                                        \
+                    p.ratio[static_cast<size_t>(sid) * p.n + vorig_at(j)] = Ra;                  \
+                    p.ratio[static_cast<size_t>(sid) * p.n + vorig_at(j + W)] = Rb;              \
+                }                                                                                \
+                newbits |= static_cast<ebits_t>((decide(Ra) ? 1u : 0u) | (decide(Rb) ? 2u : 0u)) << i; \
+            }                                                                                    \
+        }                                                                                        \
+        for (; j < end; j += W, ++i, vea += step) {                                              \
+            const double R = var_node<D>(ml, vea, p0, regular_p0);                               \
+            if (wr) p.ratio[static_cast<size_t>(sid) * p.n + vorig_at(j)] = R;                   \
+            newbits |= static_cast<ebits_t>(decide(R) ? 1u : 0u) << i;                          \
+        }                                                                                        \
+    }
+                BP_DEGREE_SWITCH(deg, BP_CASE, ;)
+#undef BP_CASE
+            }
+            // Only variables whose decision flipped touch the residual syndrome s xor H*e (:180-181, kept
+            // incrementally); every lane walks its own flips, no value comes back from the atomics.
+            ebits_t f = ebits ^ newbits;
+            ebits = newbits;
+            while (f) {
+                int b;
+                if constexpr (EB64) b = __ffsll(static_cast<long long>(f)) - 1;
+                else b = __ffs(static_cast<int>(f)) - 1;
+                f &= f - 1;
+                const int jj = warp + b * W;
+                int e0, e1;
+                if (p.uni_vdeg) { e0 = jj * p.uni_vdeg; e1 = e0 + p.uni_vdeg; }
+                else { e0 = static_cast<int>(lds_u16(colptr_a + 2 * jj)); e1 = static_cast<int>(lds_u16(colptr_a + 2 * jj + 2)); }
+                for (int e = e0; e < e1; ++e) {
+                    const uint32_t ent = lds_u16(vflip_a + 2 * e);                    // (check/32)*128 + check%32
+                    const uint32_t addr = res_a + (ent & ~127u);
+                    const uint32_t bit = 1u << (ent & 31u);
+                    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(addr), "r"(bit) : "memory");
+                }
+            }
+        }
+        if (warp == wP) cp_async_wait_all();                  // staged window complete before anyone reads it
+        __syncthreads();
+        // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)
+        uint32_t r = 0;
+        for (int w = 0; w < p.SW; ++w) r |= lds_u32(res_a + w * 128);
+        if (active) ++iter;
+        const bool conv = active && r == 0u;
+        const bool done = active && ((p.early_stop && conv) || iter >= p.max_iters);
+        const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
+        if (done) {
+            // errors[:, sid] = guess (:227): every warp ORs the set bits it owns into the pre-zeroed packed row
+            uint32_t *row = p.err_words + static_cast<size_t>(sid) * p.NW;
+            ebits_t b = ebits;
+            while (b) {
+                int bi;
+                if constexpr (EB64) bi = __ffsll(static_cast<long long>(b)) - 1;
+                else bi = __ffs(static_cast<int>(b)) - 1;
+                b &= b - 1;
+                const int j = vorig_at(warp + bi * W);
+                atomicOr(row + (j >> 5), 1u << (j & 31));
+            }
+            if (warp == wO) {
+                p.conv[sid] = conv ? 1 : 0;
+                if (p.iters) p.iters[sid] = iter;
+                n_done += 1; n_conv += conv ? 1 : 0; n_iters += iter;
+            }
+        }
+        if (done_mask) {
+            refill(done_mask);
+            any_active = __ballot_sync(0xffffffffu, active);
+        }
+    }
+
+    if (warp == wO && p.counters) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
+            n_conv += __shfl_xor_sync(0xffffffffu, n_conv, o);
+            n_iters += __shfl_xor_sync(0xffffffffu, n_iters, o);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 0, n_done);
+            atomicAdd(p.counters + 1, n_conv);
+            atomicAdd(p.counters + 2, n_iters);
+        }
+    }
+}
+
+}  // inline namespace BP_VNS
+}  // namespace bp

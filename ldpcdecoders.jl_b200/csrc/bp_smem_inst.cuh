@@ -1,0 +1,46 @@
+// bp_smem_inst.cuh -- body of one BP_VARIANT translation unit of the shared-memory-resident kernel (bp_smem.cuh).
+#include "bp_launch.h"
+#include "bp_smem.cuh"
+
+#define BPS_CAT(a, v) a##v
+#define BPS_NAME2(prefix, v) BPS_CAT(prefix, v)
+#define BPS_NAME(prefix) BPS_NAME2(prefix, BP_VARIANT)
+
+namespace bp {
+
+template <int MAXT, int MINB, bool EB64>
+static cudaError_t smem_attrs_one(int smem_bytes, int threads, int *blocks_per_sm)
+{
+    auto k = bp_smem_kernel<MAXT, MINB, EB64>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes);
+}
+
+cudaError_t BPS_NAME(smem_kernel_attrs_)(int shape, int eb64, int smem_bytes, int threads, int *bps)
+{
+    if (shape == kShape256x2) return eb64 ? smem_attrs_one<256, 2, true>(smem_bytes, threads, bps) : smem_attrs_one<256, 2, false>(smem_bytes, threads, bps);
+    if (shape == kShape384x2) return eb64 ? smem_attrs_one<384, 2, true>(smem_bytes, threads, bps) : smem_attrs_one<384, 2, false>(smem_bytes, threads, bps);
+    if (shape == kShape512x1) return eb64 ? smem_attrs_one<512, 1, true>(smem_bytes, threads, bps) : smem_attrs_one<512, 1, false>(smem_bytes, threads, bps);
+    return cudaErrorInvalidConfiguration;
+}
+
+// the shared-memory limit is (re)set before every launch: it belongs to the instantiation, not to a handle
+template <int MAXT, int MINB, bool EB64>
+static void smem_launch_one(int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p)
+{
+    auto k = bp_smem_kernel<MAXT, MINB, EB64>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return;
+    k<<<grid, threads, smem_bytes, st>>>(p);
+}
+
+void BPS_NAME(smem_kernel_launch_)(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p)
+{
+    if (shape == kShape256x2) { if (eb64) smem_launch_one<256, 2, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<256, 2, false>(grid, threads, smem_bytes, st, p); }
+    if (shape == kShape384x2) { if (eb64) smem_launch_one<384, 2, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<384, 2, false>(grid, threads, smem_bytes, st, p); }
+    if (shape == kShape512x1) { if (eb64) smem_launch_one<512, 1, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<512, 1, false>(grid, threads, smem_bytes, st, p); }
+}
+
+}  // namespace bp

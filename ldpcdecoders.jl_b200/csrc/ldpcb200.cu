@@ -143,11 +143,13 @@ struct ldpcb200 {
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
+    int opt_lean = 1;            // family SMEM: use the round-2 kernel (bp_smem.cuh) when the code fits its envelope
     // resolved configuration
     bool configured = false;
     int family = 0, mode = 0, warps = 0, ctas_per_sm = 0, smem_bytes = 0, slots = 0, shape = 0;
     int nfw = 0;                 // decision-field words per thread (0: fields live in registers)
     bool efield_global = false;
+    bool lean = false, eb64 = false;   // bp_smem_kernel selected / its decision fields are 64 bits wide
     bp::KernelParams kp_proto{};
     std::vector<DeviceCtx> dev;
     std::atomic<long long> launches{0};
@@ -187,6 +189,25 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
     p.off_ring = static_cast<int>(off);
     if (p.pd > 0) off += static_cast<long long>(threads / 32) * p.ring_warp_bytes;
     off = (off + 15) / 16 * 16;
+    return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
+}
+
+// shared-memory carve-up of bp_smem_kernel (bp_smem.cuh):
+//   messages | syn [SW][32] | resid [2][SW][32] | stage [2][SW][32] | tables | mbar
+int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p)
+{
+    long long off = static_cast<long long>(h->E) * 32 * 8;
+    p.off_syn = static_cast<int>(off);    off += h->SW * 128;
+    p.off_resid = static_cast<int>(off);  off += 2 * h->SW * 128;      // per-lane double buffer
+    p.off_stage = static_cast<int>(off);  off += 2 * h->SW * 128;      // double-buffered queue window
+    p.off_nnz = p.off_efield = 0;
+    off = (off + 15) / 16 * 16;
+    p.off_tables = static_cast<int>(off);
+    off += static_cast<long long>(h->tables.size());
+    off = (off + 7) / 8 * 8;
+    p.off_mbar = static_cast<int>(off);   off += 8;
+    off = (off + 127) / 128 * 128;
+    p.pd = 0; p.ring_slot_bytes = 0; p.ring_warp_bytes = 0; p.off_ring = static_cast<int>(off);
     return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
 }
 
@@ -564,15 +585,32 @@ int configure(ldpcb200 *h)
         if (mode < 0) return fail(LDPCB200_EUNSUPPORTED, "no kernel configuration fits in shared memory");
     }
     shape = kernel_shape(two, warps * 32);
+    // round-2 kernel for the shared-memory family: regular-enough codes whose decisions fit in a register per warp
+    bool lean = false, eb64 = false;
+    if (mode == 0 && h->opt_lean && !h->big && nfw == 0 && h->segs.ncseg > 0 && h->segs.nvseg > 0) {
+        bp::KernelParams kl{};
+        const int need_l = smem_layout_lean(h, kl);
+        if (need_l <= (two ? per_cta_2 : d0.smem_optin)) {
+            lean = true; need = need_l; kp = kl;
+            eb64 = (h->n + warps - 1) / warps > 32;
+        }
+    }
     int bps = 0, rc;
     for (DeviceCtx &d : h->dev) {
         CU(cudaSetDevice(d.device));
-        rc = kernel_attrs_dispatch(h->variant, mode, h->big, shape, need, warps * 32, &bps);
-        if (rc) return rc;
+        if (lean) {
+            cudaError_t e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_kernel_attrs_1(shape, eb64, need, warps * 32, &bps)
+                                                                  : bp::smem_kernel_attrs_0(shape, eb64, need, warps * 32, &bps);
+            if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "kernel attributes (shared-memory kernel): %s", cudaGetErrorString(e));
+        } else {
+            rc = kernel_attrs_dispatch(h->variant, mode, h->big, shape, need, warps * 32, &bps);
+            if (rc) return rc;
+        }
     }
     if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "BP kernel (mode %d, %d threads, %d B smem) does not fit on an SM", mode, warps * 32, need);
     h->family = family; h->mode = mode; h->warps = warps; h->shape = shape; h->ctas_per_sm = bps;
     h->smem_bytes = need; h->nfw = nfw; h->efield_global = ef_global; h->kp_proto = kp;
+    h->lean = lean; h->eb64 = eb64;
     h->slots = 32 * bps * d0.sm_count;
     h->configured = true;
     return 0;
@@ -656,8 +694,24 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     }
     // finished lanes OR their set decision bits into the row: rows start out zero
     CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
-    kernel_launch_dispatch(h->variant, h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
-    h->launches++;
+    if (h->lean) {
+        // 32-bit queue arithmetic inside the kernel: at most 2^30 syndromes per launch
+        const int64_t kMaxLaunch = 1ll << 30;
+        for (int64_t b0 = 0; b0 < B; b0 += kMaxLaunch) {
+            const int64_t Bl = std::min(kMaxLaunch, B - b0);
+            bp::KernelParams q = p;
+            q.B = Bl;
+            q.syn_words = syn_words + b0 * h->SW; q.err_words = err_words + b0 * h->NW; q.conv = conv + b0;
+            q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
+            const int gl = static_cast<int>(std::min<long long>((Bl + 31) / 32, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
+            if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_kernel_launch_1(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+            else bp::smem_kernel_launch_0(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+            h->launches++;
+        }
+    } else {
+        kernel_launch_dispatch(h->variant, h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
+        h->launches++;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1079,6 +1133,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
+    else if (k == "lean") h->opt_lean = value ? 1 : 0;
     else if (k == "slots") h->opt_slots = static_cast<int>(value);   // accepted for compatibility, unused
     else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
     h->configured = false;
@@ -1104,6 +1159,8 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
                              : static_cast<int64_t>(h->slots) * std::max<int64_t>(h->E, 1) * 8;
     out->kernel_mode = h->mode;
     out->prefetch_distance = h->kp_proto.pd;
+    out->kernel_rev = h->lean ? 2 : 1;
+    out->counters_via_nccl = 0;
     return 0;
 }
 

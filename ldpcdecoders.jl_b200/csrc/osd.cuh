@@ -164,10 +164,14 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
         }
         __syncthreads();
         int npiv = 0, steps = 0;
+        int tog = 0;                                      // exchange buffer of this trip: flips on EVERY trip (a column skip may
+                                                          // land on a column of the same parity, so `j & 1` would reuse the buffer
+                                                          // a slow warp is still reading)
         for (int j = 0; j < n; ++j) {
             const int wj = j >> 5;
             const uint32_t bj = 1u << (j & 31);
-            int *wb = wcnts + (j & 1) * 96;               // per warp: [0..31] hits, [32..63] smallest hit row, [64..95] later bits
+            int *wb = wcnts + tog * 96;                   // per warp: [0..31] hits, [32..63] smallest hit row, [64..95] later bits
+            tog ^= 1;
             int cand = 0x7fffffff, total = 0;
             uint32_t hbs[RPT], later = 0;                 // later: bits above j (same word) set in any unused row
 #pragma unroll

@@ -62,6 +62,13 @@ def test_parity_configs(pkg, oracle, codes, name, per, B, families):
         g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True)
         assert g["info"]["family"] == fam
         assert_same(g, ref, want_ratio=True)
+        if fam == SMEM:
+            # the shared-memory family has two kernels: the round-2 one (default where the code fits its envelope)
+            # and the general persistent kernel (lean = 0); both must replay the reference bit for bit
+            assert g["info"]["kernel_rev"] == 2, g["info"]
+            g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True, lean=0)
+            assert g["info"]["kernel_rev"] == 1
+            assert_same(g, ref, want_ratio=True)
 
 
 def test_parity_c5_large_code(pkg, oracle, codes):
@@ -98,6 +105,8 @@ def test_ragged_batches(pkg, oracle, codes, B, fam):
     ref = oracle.batch_decode(H, 0.06, mi, syn)
     # small_batch = 0: keep these small batches on the persistent (lane-per-syndrome) kernel
     assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0), ref)
+    if fam == SMEM:
+        assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0, lean=0), ref)
 
 
 @pytest.mark.parametrize("fam", [SMEM, GLOBAL])
@@ -355,22 +364,59 @@ def test_staging_depths_agree(pkg, oracle, codes):
         assert_same(run_gpu(pkg, H, 0.04, mi, syn, prefetch=pf), ref)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_in_library_sharding_over_two_devices(pkg, oracle, codes):
-    """devices = [0, 1]: the library splits the batch into contiguous column ranges (boundaries
-    multiples of 32) and sums the counters; results equal the single-device ones."""
+def shard_device_sets():
+    """Device lists for the in-library sharding tests.  With one visible GPU the same device is listed
+    several times: the threaded split, the shard-boundary alignment of the bit formats and the counter
+    summation run exactly as they do over distinct devices (each entry has its own streams and buffers)."""
+    nd = torch.cuda.device_count()
+    sets = [[0, 0], [0, 0, 0]]
+    if nd >= 2:
+        sets.append(list(range(min(nd, 8))))
+    return sets
+
+
+@pytest.mark.parametrize("fmt", ["u8", "bits", "packed", "i64"])
+def test_in_library_sharding_over_devices(pkg, oracle, codes, fmt):
+    """devices = [d0, d1, ...]: the library splits the batch into contiguous column ranges (boundaries
+    multiples of 32) and sums the counters; results equal the single-device ones
+    (batchdecode! semantics, belief_propagation.jl:220-231, for every boundary format)."""
     H, _, mi = codes.config_matrix("C3")
+    s, n = H.shape
     B = 100_003
     _, syn = oracle.sample(H, 0.05, 77, 0, B)
     ref = oracle.batch_decode(H, 0.05, mi, syn, nthreads=oracle.num_threads())
-    dec = pkg.BeliefPropagationDecoder(H, 0.05, mi, devices=[0, 1])
-    assert dec.info()["ndev"] == 2
-    errors = np.zeros((H.shape[1], B), dtype=np.uint8, order="F")
-    iters = np.zeros(B, dtype=np.int32)
-    _, success = pkg.batchdecode_b(dec, syn, errors, iters=iters)
-    g = dict(errors=errors, converged=success, iters=iters, counters=dec.last_counters)
-    dec.close()
-    assert_same(g, ref)
+    lib = pkg._lib
+    for devs in shard_device_sets():
+        dec = pkg.BeliefPropagationDecoder(H, 0.05, mi, devices=devs)
+        info = dec.info()
+        assert info["ndev"] == len(devs)
+        iters = np.zeros(B, dtype=np.int32)
+        if fmt in ("u8", "i64"):
+            dt = np.uint8 if fmt == "u8" else np.int64
+            errors = np.zeros((n, B), dtype=dt, order="F")
+            _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn.astype(dt)), errors, iters=iters)
+            got = errors.astype(np.uint8)
+        elif fmt == "bits":
+            sin = np.packbits(syn.T.reshape(-1), bitorder="little")           # bit c*s + r of the stream
+            sin = np.concatenate([sin, np.zeros((-len(sin)) % 8, np.uint8)])
+            eout = np.zeros((B * n + 63) // 64 * 8, dtype=np.uint8)
+            conv = np.zeros(B, dtype=np.uint8)
+            dec.last_counters = dec.decode_raw(B, sin, lib.FMT_BITS, 0, eout, lib.FMT_BITS, 0, conv, iters)
+            got = np.unpackbits(eout, bitorder="little")[:B * n].reshape(B, n).T
+            success = conv.astype(bool)
+        else:
+            SW, NW = info["syn_words"], info["err_words"]
+            pad = np.zeros((SW * 32, B), np.uint8)
+            pad[:s] = syn
+            sin = np.packbits(pad.T.reshape(B, SW * 32), axis=1, bitorder="little").view(np.uint32).reshape(B, SW)
+            eout = np.zeros((B, NW), dtype=np.uint32)
+            conv = np.zeros(B, dtype=np.uint8)
+            dec.last_counters = dec.decode_raw(B, np.ascontiguousarray(sin), lib.FMT_PACKED32, SW, eout, lib.FMT_PACKED32, NW, conv, iters)
+            got = np.unpackbits(eout.view(np.uint8).reshape(B, NW * 4), axis=1, bitorder="little")[:, :n].T
+            success = conv.astype(bool)
+        g = dict(errors=got, converged=success, iters=iters, counters=dec.last_counters)
+        dec.close()
+        assert_same(g, ref)
 
 
 def run_gpu_variant(pkg, H, per, max_iters, syn, variant, **opts):
@@ -648,15 +694,38 @@ def test_small_batch_host_path_all_formats(pkg, oracle, codes, B):
     dm.close()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_bposd_in_library_sharding_over_two_devices(pkg, oracle, codes):
+def test_bposd_in_library_sharding_over_devices(pkg, oracle, codes):
     H, _, mi = codes.config_matrix("C3")
     B = 5000
     _, syn = oracle.sample(H, 0.08, 1234, 0, B)
     ref = oracle.bposd_decode(H, 0.08, mi, syn, nthreads=oracle.num_threads())
-    g = run_gpu_bposd(pkg, H, 0.08, mi, syn, devices=[0, 1])
-    assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
-    assert g["stats"][0] == int((~ref["converged"]).sum()) and g["counters"][0] == B
+    for devs in shard_device_sets():
+        g = run_gpu_bposd(pkg, H, 0.08, mi, syn, devices=devs)
+        assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"])
+        assert g["stats"][0] == int((~ref["converged"]).sum()) and g["counters"][0] == B
+
+
+def test_two_live_decoders_with_different_shared_memory_sizes(pkg, oracle, codes):
+    """Two handles that share a kernel instantiation but need different dynamic shared-memory sizes (surface-15 and
+    the gross code, both family SMEM, 256-thread shape) decode alternately: the limit is an attribute of the
+    instantiation, not of a handle, so it must be set per launch."""
+    Ha, _, mi = codes.config_matrix("C3")
+    Hb, _, _ = codes.config_matrix("C2")
+    for lean in (1, 0):
+        da = pkg.BeliefPropagationDecoder(Ha, 0.05, mi, lean=lean, warps=8)
+        db = pkg.BeliefPropagationDecoder(Hb, 0.03, mi, lean=lean, warps=8)
+        assert da.info()["smem_bytes"] != db.info()["smem_bytes"]
+        _, sa = oracle.sample(Ha, 0.05, 5, 0, 2000)
+        _, sb = oracle.sample(Hb, 0.03, 6, 0, 2000)
+        ra = oracle.batch_decode(Ha, 0.05, mi, sa, nthreads=oracle.num_threads())
+        rb = oracle.batch_decode(Hb, 0.03, mi, sb, nthreads=oracle.num_threads())
+        for _ in range(2):
+            for dec, H, syn, ref in ((da, Ha, sa, ra), (db, Hb, sb, rb), (da, Ha, sa, ra)):
+                errors = np.zeros((H.shape[1], syn.shape[1]), dtype=np.uint8, order="F")
+                _, success = pkg.batchdecode_b(dec, syn, errors)
+                assert np.array_equal(errors, ref["errors"]) and np.array_equal(success, ref["converged"])
+        da.close()
+        db.close()
 
 
 @pytest.mark.parametrize("name,per,B", [("C3", 0.05, 60), ("C4", 0.04, 20), ("C1", 0.04, 9), ("C2", 0.03, 148)])
