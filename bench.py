@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--family", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1)
+    ap.add_argument("--kernel-profile", action="store_true", dest="kernel_profile",
+                    help="phase timing of the shared-memory kernel (adds clock reads; not a bench value)")
+    ap.add_argument("--max-ctas", type=int, default=0, dest="max_ctas", help="cap on resident CTAs per SM (experiments)")
     ap.add_argument("--lean", type=int, default=-1, help="family SMEM: 1 = round-2 kernel (default), 0 = general persistent kernel")
     ap.add_argument("--variant", default="exact", choices=["exact", "minsum"],
                     help="exact = reference-parity sum-product (headline); minsum = normalised min-sum (no reference equivalent)")
@@ -252,6 +255,10 @@ def main():
         opts["prefetch"] = args.prefetch
     if args.lean >= 0:
         opts["lean"] = args.lean
+    if args.max_ctas > 0:
+        opts["max_ctas_per_sm"] = args.max_ctas
+    if args.kernel_profile:
+        opts["kernel_profile"] = 1
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant=args.variant, **opts)
     info = dec.info()
     SW, NW = info["syn_words"], info["err_words"]
@@ -371,6 +378,11 @@ def main():
             "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
             "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "smem_bytes", "slots",
                                             "message_bytes", "prefetch_distance", "kernel_rev")}}
+
+    if args.kernel_profile:
+        kp = dec.kernel_profile()
+        wi = max(kp["warp_iterations"], 1)
+        line["kernel_profile_cycles_per_warp_iteration"] = {k: round(v / wi, 1) for k, v in kp.items() if k != "warp_iterations"}
 
     # ---- end to end through the host-buffer C-ABI call (Julia BitMatrix in / out), pinned memory
     if not args.no_e2e:

@@ -183,6 +183,12 @@ int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
  * back 0.  Test hook, not part of the decode path. */
 int ldpcb200_selftest_division(int32_t device, int32_t mode, uint64_t n, uint64_t seed, uint64_t *mismatches);
 
+/* Phase timing of the shared-memory kernel (option "kernel_profile" = 1 before the decodes): out8 receives SM cycles
+ * summed over all warps since the last reset -- [0] check pass, [1] wait at the barrier after it, [2] variable pass,
+ * [3] residual-syndrome updates of flipped decisions, [4] wait at the second barrier, [5] syndrome re-check + outputs,
+ * [6] refill -- and [7] the number of warp-iterations.  Synchronises the device.  Diagnostics, not part of the path. */
+int ldpcb200_kernel_profile(ldpcb200_t *h, int32_t dev_slot, int64_t *out8, int32_t reset);
+
 /* Number of kernels of this library launched through the handle so far (bench bookkeeping). */
 int ldpcb200_launch_count(const ldpcb200_t *h, int64_t *out);
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "ldpcb200_destroy", "ldpcb200_info", "ldpcb200_set_option", "ldpcb200_decode_batch",
     "ldpcb200_decode_device", "ldpcb200_sample_device", "ldpcb200_score_device",
     "ldpcb200_launch_count", "ldpcb200_selftest_division",
-    "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device",
+    "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device", "ldpcb200_kernel_profile",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     lib.ldpcb200_osd0_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.ldpcb200_sample_device.argtypes = [vp, i32, i64, i64, u64, dbl, vp, vp, vp]
     lib.ldpcb200_score_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.ldpcb200_kernel_profile.argtypes = [vp, i32, ctypes.POINTER(i64), i32]
     lib.ldpcb200_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ldpcb200_selftest_division.argtypes = [i32, i32, u64, u64, ctypes.POINTER(u64)]   # mismatches[4]
     for name in SYMBOLS:

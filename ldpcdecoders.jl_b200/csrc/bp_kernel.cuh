@@ -67,11 +67,13 @@ struct KernelParams {
     double *ratio;                // [B][n] or null
     int ratio_last_only;          // 1: write ratios only in iteration max_iters
     unsigned long long *counters; // [4] or null
+    unsigned long long *prof;     // bp_smem_kernel: null, or [8] phase cycle sums (check, wait B1, variable, flips, wait B2, done+emit, refill, iterations)
     // narrow tables (modes 0/1), copied to shared memory:
     const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
     int tables_bytes;             // multiple of 16
     int off_colptr, off_ve, off_vflip;   // byte offsets inside the blob (rowptr at 0)
     int off_corig, off_vorig;            // u16 original ids of the kernels' check / variable order (if permuted)
+    int cv_cpw, cv_stride;               // bp_smem_kernel, contiguous variable ownership: variables per warp (0 = interleaved), bytes per warp in the ve table
     int perm_c, perm_v;                  // node order differs from the caller's (degree-sorted)
     Segments seg;
     // wide tables (mode 2), read from global memory:

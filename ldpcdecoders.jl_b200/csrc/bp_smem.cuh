@@ -25,7 +25,52 @@
 namespace bp {
 inline namespace BP_VNS {
 
-template <int MAXT, int MINB, bool EB64>
+__device__ __forceinline__ uint4 lds_u128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+// NV variables of degree D whose NV*D slot offsets are consecutive in the table at `ta` (16-byte aligned when NV == 4):
+// loads, products, one NaN test for all of them (bp_math.cuh: var_products), stores.  R[] receives the posterior ratios.
+template <int D, int NV>
+__device__ __forceinline__ void var_group(uint32_t ml, uint32_t ta, double p0, bool regular_p0, double (&R)[NV])
+{
+    uint32_t off[NV * D];
+    if constexpr (NV == 4) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            const uint4 v = lds_u128(ta + 16 * q);
+            off[4 * q] = v.x; off[4 * q + 1] = v.y; off[4 * q + 2] = v.z; off[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV * D; ++q) off[q] = lds_u32(ta + 4 * q);
+    }
+    double m[NV][D], o[NV][D];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < D; ++k) m[v][k] = ld_msg(ml + off[v * D + k]);
+    uint32_t flag = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) flag = max(flag, var_products<D>(m[v], p0, o[v], R[v]));
+    if (var_products_suspect(flag) || !regular_p0) {       // rare: some running product is NaN -- the clamped sequence
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            R[v] = var_update_clamped<D>(m[v], p0);
+#pragma unroll
+            for (int k = 0; k < D; ++k) o[v][k] = m[v][k];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < D; ++k) st_msg(ml + off[v * D + k], o[v][k]);
+}
+
+template <int MAXT, int MINB, bool EB64, bool PROF = false>
 __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_constant__ KernelParams p)
 {
     using ebits_t = typename std::conditional<EB64, unsigned long long, uint32_t>::type;
@@ -46,6 +91,12 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     const uint32_t corig_a = sbase + p.off_tables + p.off_corig;
     const uint32_t vorig_a = sbase + p.off_tables + p.off_vorig;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
+
+    // contiguous variable ownership (uniform variable degree, caller's variable order): bit i of a warp's decision
+    // field is variable vbase + i; otherwise variables are dealt round-robin (bit i <-> warp + i*W)
+    const bool cv = p.cv_cpw > 0;
+    const int vbase = warp * p.cv_cpw;
+    const int vcnt = cv ? max(0, min(p.cv_cpw, p.n - vbase)) : 0;
 
     auto vorig_at = [&](int j) -> int { return p.perm_v ? static_cast<int>(lds_u16(vorig_a + 2 * j)) : j; };
 
@@ -115,6 +166,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     const double p0 = p.p0;
     const double caux = p.check_aux;
     const bool regular_p0 = p.regular_p0;
+    // optional phase timing (option "kernel_profile"): SM cycles per warp summed over all warps
+    constexpr bool prof = PROF;                            // compiled into one extra instantiation only (bp_smem_inst.cuh)
+    uint32_t pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;     // 32-bit sums: a warp's share of one launch stays far below 2^32 cycles
+    auto tick = [&](int k) {
+        if constexpr (prof) { const uint32_t t = static_cast<uint32_t>(clock64()); pc[k] += t - pt; pt = t; }
+    };
+    if constexpr (prof) pt = static_cast<uint32_t>(clock64());
     while (any_active != 0u) {
         // ------------------------------------------------------------------ check pass (:135-150)
         if (active) {
@@ -141,11 +199,41 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         }
         fresh = false;
         syn_a = syn_own;                                   // (wS copied the staged syndrome into the lane's own rows at refill time)
+        tick(0);
         __syncthreads();
+        tick(1);
         // --------------------------------------------------------------- variable pass (:152-178)
         if (active) {
             ebits_t newbits = 0;
             const bool wr = p.ratio != nullptr && (!p.ratio_last_only || iter + 1 >= p.max_iters);
+            if (cv) {
+                // contiguous ownership: this warp's variables are vbase .. vbase + vcnt - 1 (bit i <-> vbase + i); four per trip
+#define BP_CASE(D)                                                                               \
+    {                                                                                            \
+        uint32_t ta = ve_a + warp * p.cv_stride;                                                 \
+        int i = 0;                                                                               \
+        if constexpr (D <= 4) {                                                                  \
+            for (; i + 4 <= vcnt; i += 4, ta += 16 * D) {                                        \
+                double R[4];                                                                     \
+                var_group<D, 4>(ml, ta, p0, regular_p0, R);                                      \
+                if (wr) {                                                                        \
+                    double *rr = p.ratio + static_cast<size_t>(sid) * p.n + vbase + i;           \
+                    rr[0] = R[0]; rr[1] = R[1]; rr[2] = R[2]; rr[3] = R[3];                      \
+                }                                                                                \
+                const uint32_t nib = (decide(R[0]) ? 1u : 0u) | (decide(R[1]) ? 2u : 0u) | (decide(R[2]) ? 4u : 0u) | (decide(R[3]) ? 8u : 0u); \
+                newbits |= static_cast<ebits_t>(nib) << i;                                       \
+            }                                                                                    \
+        }                                                                                        \
+        for (; i < vcnt; ++i, ta += 4 * D) {                                                     \
+            double R[1];                                                                         \
+            var_group<D, 1>(ml, ta, p0, regular_p0, R);                                          \
+            if (wr) p.ratio[static_cast<size_t>(sid) * p.n + vbase + i] = R[0];                  \
+            newbits |= static_cast<ebits_t>(decide(R[0]) ? 1u : 0u) << i;                       \
+        }                                                                                        \
+    }
+                BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
+#undef BP_CASE
+            } else {
             int j = warp, i = 0;
             for (int g = 0; g < p.seg.nvseg; ++g) {
                 const int deg = p.seg.vdeg[g], first = p.seg.vfirst[g], end = p.seg.vend[g], eb = p.seg.vedge[g];
@@ -188,10 +276,28 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
                 BP_DEGREE_SWITCH(deg, BP_CASE, ;)
 #undef BP_CASE
             }
+            }
             // Only variables whose decision flipped touch the residual syndrome s xor H*e (:180-181, kept
             // incrementally); every lane walks its own flips, no value comes back from the atomics.
             ebits_t f = ebits ^ newbits;
             ebits = newbits;
+            tick(2);
+            if (cv) {
+#define BP_CASE(D)                                                                               \
+    while (f) {                                                                                  \
+        int b;                                                                                   \
+        if constexpr (EB64) b = __ffsll(static_cast<long long>(f)) - 1;                          \
+        else b = __ffs(static_cast<int>(f)) - 1;                                                 \
+        f &= f - 1;                                                                              \
+        const uint32_t fa = vflip_a + 2 * D * (vbase + b);                                       \
+        uint32_t ent[D];                                                                         \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) ent[k] = lds_u16(fa + 2 * k);              \
+        _Pragma("unroll") for (int k = 0; k < D; ++k)                                            \
+            asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(res_a + (ent[k] & ~127u)), "r"(1u << (ent[k] & 31u)) : "memory"); \
+    }
+                BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
+#undef BP_CASE
+            }
             while (f) {
                 int b;
                 if constexpr (EB64) b = __ffsll(static_cast<long long>(f)) - 1;
@@ -209,8 +315,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
                 }
             }
         }
+        tick(3);
         if (warp == wP) cp_async_wait_all();                  // staged window complete before anyone reads it
         __syncthreads();
+        tick(4);
         // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)
         uint32_t r = 0;
         for (int w = 0; w < p.SW; ++w) r |= lds_u32(res_a + w * 128);
@@ -222,6 +330,19 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
             // errors[:, sid] = guess (:227): every warp ORs the set bits it owns into the pre-zeroed packed row
             uint32_t *row = p.err_words + static_cast<size_t>(sid) * p.NW;
             ebits_t b = ebits;
+            if (cv) {                                         // the field is bits vbase .. vbase+vcnt-1 of the row
+                uint32_t *w0 = row + (vbase >> 5);
+                const int lo = vbase & 31;
+                const unsigned long long v = static_cast<unsigned long long>(b) << lo;
+                const uint32_t v0 = static_cast<uint32_t>(v), v1 = static_cast<uint32_t>(v >> 32);
+                if (v0) atomicOr(w0, v0);
+                if (v1) atomicOr(w0 + 1, v1);
+                if constexpr (EB64) {
+                    const uint32_t v2 = lo ? static_cast<uint32_t>(static_cast<unsigned long long>(b) >> (64 - lo)) : 0u;
+                    if (v2) atomicOr(w0 + 2, v2);
+                }
+                b = 0;
+            }
             while (b) {
                 int bi;
                 if constexpr (EB64) bi = __ffsll(static_cast<long long>(b)) - 1;
@@ -236,11 +357,16 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
                 n_done += 1; n_conv += conv ? 1 : 0; n_iters += iter;
             }
         }
+        tick(5);
         if (done_mask) {
             refill(done_mask);
             any_active = __ballot_sync(0xffffffffu, active);
         }
+        tick(6);
+        if constexpr (prof) pc[7] += 1;
     }
+    if (prof && p.prof != nullptr && lane == 0)
+        for (int k = 0; k < 8; ++k) atomicAdd(p.prof + k, static_cast<unsigned long long>(pc[k]));
 
     if (warp == wO && p.counters) {
         for (int o = 16; o > 0; o >>= 1) {

@@ -38,6 +38,12 @@ static void smem_launch_one(int grid, int threads, int smem_bytes, cudaStream_t 
 
 void BPS_NAME(smem_kernel_launch_)(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p)
 {
+    if (shape == kShape256x2 && !eb64 && p.prof != nullptr) {      // phase-timing build (diagnostics)
+        auto k = bp_smem_kernel<256, 2, false, true>;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return;
+        k<<<grid, threads, smem_bytes, st>>>(p);
+        return;
+    }
     if (shape == kShape256x2) { if (eb64) smem_launch_one<256, 2, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<256, 2, false>(grid, threads, smem_bytes, st, p); }
     if (shape == kShape384x2) { if (eb64) smem_launch_one<384, 2, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<384, 2, false>(grid, threads, smem_bytes, st, p); }
     if (shape == kShape512x1) { if (eb64) smem_launch_one<512, 1, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<512, 1, false>(grid, threads, smem_bytes, st, p); }

@@ -112,7 +112,7 @@ struct DeviceCtx {
         DevBuf osd_list, osd_ctl;            // OSD-0: unconverged list, {count, queue}
     } set[2];
     cudaEvent_t decode_done = nullptr;
-    DevBuf counters, scratch, osd_stats;
+    DevBuf counters, scratch, osd_stats, kprof;
     DevBuf tiny;            // small-batch host calls: one device block ...
     PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
@@ -135,6 +135,10 @@ struct ldpcb200 {
     bp::Segments segs{};
     std::vector<unsigned char> tables;   // SMEM-family blob
     int off_colptr = 0, off_ve = 0, off_vflip = 0, off_corig = 0, off_vorig = 0;
+    int cv_cpw = 0, cv_stride = 0;       // contiguous variable ownership of bp_smem_kernel: variables per warp, bytes per warp in the ve table
+    int tables_cv_warps = 0;             // layout the device copies of `tables` currently have
+    bool tables_dirty = false;           // host blob rebuilt, device copies stale
+    int opt_cv = 1;                      // bp_smem_kernel: contiguous variable ownership where the code allows it
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
@@ -143,6 +147,8 @@ struct ldpcb200 {
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
+    int opt_kernel_profile = 0;  // bp_smem_kernel adds per-phase SM cycles to the handle's profile block (ldpcb200_kernel_profile)
+    int opt_max_ctas = 0;        // cap on resident CTAs per SM (0: whatever fits; experiments)
     int opt_lean = 1;            // family SMEM: use the round-2 kernel (bp_smem.cuh) when the code fits its envelope
     // resolved configuration
     bool configured = false;
@@ -209,6 +215,65 @@ int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p)
     off = (off + 127) / 128 * 128;
     p.pd = 0; p.ring_slot_bytes = 0; p.ring_warp_bytes = 0; p.off_ring = static_cast<int>(off);
     return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
+}
+
+// SMEM-family table blob (copied to shared memory by one TMA bulk copy): rowptr u16[s+1] | colptr u16[n+1] |
+// ve_off u32 (slot * 256 bytes per edge, variable-major) | vflip u16[E] | corig u16[s] | vorig u16[n], all in the
+// kernels' node order.  cv_warps > 0 (bp_smem_kernel with contiguous variable ownership, uniform variable degree D):
+// the ve_off section is laid out per warp -- warp w's cpw = ceil(n / cv_warps) variables start at
+// w * cv_stride bytes, cv_stride a multiple of 16 -- so that the offsets of four variables are D aligned 16-byte loads.
+void build_tables(ldpcb200 *h, int cv_warps)
+{
+    const int64_t s = h->s, n = h->n, E = h->E;
+    h->tables.clear();
+    h->cv_cpw = 0; h->cv_stride = 0;
+    if (!(E <= 0xffff && s <= 16384 && n <= 0xffff)) return;
+    int ve_bytes = static_cast<int>(4 * E);
+    if (cv_warps > 0) {
+        h->cv_cpw = static_cast<int>((n + cv_warps - 1) / cv_warps);
+        h->cv_stride = align_up(h->cv_cpw * h->uni_vdeg * 4, 16);
+        ve_bytes = cv_warps * h->cv_stride;
+    }
+    const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
+    const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 16);
+    const int o_fl = o_ve + ve_bytes;
+    const int o_co = align_up(o_fl + static_cast<int>(2 * E), 4);
+    const int o_vo = o_co + (h->perm_c ? static_cast<int>(2 * s) : 0);
+    const int total = align_up(o_vo + (h->perm_v ? static_cast<int>(2 * n) : 0), 16);
+    h->tables.assign(std::max(total, 16), 0);
+    uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
+    uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
+    uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
+    for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->p_rowptr[i]);
+    for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->p_colptr[j]);
+    uint16_t *fl = reinterpret_cast<uint16_t *>(h->tables.data() + o_fl);
+    for (int64_t e = 0; e < E; ++e) {
+        // residual-syndrome word (byte offset of its 128 B row) | bit: needs s <= 16384
+        fl[e] = static_cast<uint16_t>((h->p_ve_chk[e] >> 5) * 128 + (h->p_ve_chk[e] & 31));
+    }
+    if (cv_warps > 0) {
+        const int D = h->uni_vdeg;
+        for (int64_t j = 0; j < n; ++j) {
+            const int w = static_cast<int>(j / h->cv_cpw), i = static_cast<int>(j % h->cv_cpw);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve + w * h->cv_stride) + i * D;
+            for (int k = 0; k < D; ++k) dst[k] = static_cast<uint32_t>(h->p_ve_slot[j * D + k]) * 256u;
+        }
+    } else {
+        for (int64_t e = 0; e < E; ++e) ve[e] = static_cast<uint32_t>(h->p_ve_slot[e]) * 256u;
+    }
+    if (h->perm_c) {
+        uint16_t *co = reinterpret_cast<uint16_t *>(h->tables.data() + o_co);
+        for (int64_t i = 0; i < s; ++i) co[i] = static_cast<uint16_t>(h->corig[i]);
+    }
+    if (h->perm_v) {
+        uint16_t *vo = reinterpret_cast<uint16_t *>(h->tables.data() + o_vo);
+        for (int64_t j = 0; j < n; ++j) vo[j] = static_cast<uint16_t>(h->vorig[j]);
+    }
+    h->off_colptr = o_col;
+    h->off_ve = o_ve;
+    h->off_vflip = o_fl;
+    h->off_corig = o_co;
+    h->off_vorig = o_vo;
 }
 
 int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int base)
@@ -330,41 +395,7 @@ int build_graph(ldpcb200 *h, const int64_t *colptr, const int64_t *rowval, int b
             }
         }
     }
-    // SMEM-family blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] (slot * 256 bytes) | vflip u16[E]
-    //                   | corig u16[s] | vorig u16[n]      (all in the kernels' node order)
-    if (E <= 0xffff && s <= 16384 && n <= 0xffff) {
-        const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
-        const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 4);
-        const int o_fl = o_ve + static_cast<int>(4 * E);
-        const int o_co = align_up(o_fl + static_cast<int>(2 * E), 4);
-        const int o_vo = o_co + (h->perm_c ? static_cast<int>(2 * s) : 0);
-        const int total = align_up(o_vo + (h->perm_v ? static_cast<int>(2 * n) : 0), 16);
-        h->tables.assign(std::max(total, 16), 0);
-        uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
-        uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
-        uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
-        for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->p_rowptr[i]);
-        for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->p_colptr[j]);
-        uint16_t *fl = reinterpret_cast<uint16_t *>(h->tables.data() + o_fl);
-        for (int64_t e = 0; e < E; ++e) {
-            ve[e] = static_cast<uint32_t>(h->p_ve_slot[e]) * 256u;
-            // residual-syndrome word (byte offset of its 128 B row) | bit: needs s <= 16384
-            fl[e] = static_cast<uint16_t>((h->p_ve_chk[e] >> 5) * 128 + (h->p_ve_chk[e] & 31));
-        }
-        if (h->perm_c) {
-            uint16_t *co = reinterpret_cast<uint16_t *>(h->tables.data() + o_co);
-            for (int64_t i = 0; i < s; ++i) co[i] = static_cast<uint16_t>(h->corig[i]);
-        }
-        if (h->perm_v) {
-            uint16_t *vo = reinterpret_cast<uint16_t *>(h->tables.data() + o_vo);
-            for (int64_t j = 0; j < n; ++j) vo[j] = static_cast<uint16_t>(h->vorig[j]);
-        }
-        h->off_colptr = o_col;
-        h->off_ve = o_ve;
-        h->off_vflip = o_fl;
-        h->off_corig = o_co;
-        h->off_vorig = o_vo;
-    }
+    build_tables(h, 0);
     return 0;
 }
 
@@ -423,7 +454,7 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny}) b->release();
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
         for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
@@ -587,13 +618,38 @@ int configure(ldpcb200 *h)
     shape = kernel_shape(two, warps * 32);
     // round-2 kernel for the shared-memory family: regular-enough codes whose decisions fit in a register per warp
     bool lean = false, eb64 = false;
+    int want_cv = 0;                 // contiguous variable ownership (uniform variable degree, caller's variable order)
     if (mode == 0 && h->opt_lean && !h->big && nfw == 0 && h->segs.ncseg > 0 && h->segs.nvseg > 0) {
-        bp::KernelParams kl{};
-        const int need_l = smem_layout_lean(h, kl);
-        if (need_l <= (two ? per_cta_2 : d0.smem_optin)) {
-            lean = true; need = need_l; kp = kl;
-            eb64 = (h->n + warps - 1) / warps > 32;
+        const int budget = two ? per_cta_2 : d0.smem_optin;
+        if (h->uni_vdeg && !h->perm_v && h->opt_cv) want_cv = warps;
+        for (int attempt = 0; attempt < 2 && !lean; ++attempt) {
+            if (h->tables_cv_warps != want_cv) { build_tables(h, want_cv); h->tables_cv_warps = want_cv; h->tables_dirty = true; }
+            bp::KernelParams kl{};
+            const int need_l = smem_layout_lean(h, kl);
+            if (need_l <= budget) {
+                lean = true; need = need_l; kp = kl;
+                eb64 = (h->n + warps - 1) / warps > 32;
+            } else if (want_cv) {
+                want_cv = 0;          // the padded table does not fit: interleaved ownership
+            } else {
+                break;
+            }
         }
+    }
+    if (!lean && h->tables_cv_warps != 0) { build_tables(h, 0); h->tables_cv_warps = 0; h->tables_dirty = true; }
+    if (h->tables_dirty) {
+        for (DeviceCtx &d : h->dev) {
+            CU(cudaSetDevice(d.device));
+            CU(cudaStreamSynchronize(d.stream));
+            if (d.d_tables) CU(cudaFree(d.d_tables));
+            d.d_tables = nullptr;
+            if (!h->tables.empty()) {
+                CU(cudaMalloc(&d.d_tables, h->tables.size()));
+                CU(cudaMemcpy(d.d_tables, h->tables.data(), h->tables.size(), cudaMemcpyHostToDevice));
+            }
+        }
+        h->tables_dirty = false;
+        CU(cudaSetDevice(d0.device));
     }
     int bps = 0, rc;
     for (DeviceCtx &d : h->dev) {
@@ -608,6 +664,7 @@ int configure(ldpcb200 *h)
         }
     }
     if (bps < 1) return fail(LDPCB200_EUNSUPPORTED, "BP kernel (mode %d, %d threads, %d B smem) does not fit on an SM", mode, warps * 32, need);
+    if (h->opt_max_ctas > 0) bps = std::min(bps, h->opt_max_ctas);
     h->family = family; h->mode = mode; h->warps = warps; h->shape = shape; h->ctas_per_sm = bps;
     h->smem_bytes = need; h->nfw = nfw; h->efield_global = ef_global; h->kp_proto = kp;
     h->lean = lean; h->eb64 = eb64;
@@ -674,6 +731,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     p.counters = counters;
     p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
     p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
+    p.cv_cpw = h->lean ? h->cv_cpw : 0; p.cv_stride = h->cv_stride;
     p.g_rowptr = d.d_p_rowptr; p.g_colptr = d.d_p_colptr; p.g_ve_off = d.d_ve_off; p.g_vflip = d.d_vflip;
     p.g_corig = d.d_corig; p.g_vorig = d.d_vorig;
     p.perm_c = h->perm_c; p.perm_v = h->perm_v; p.off_corig = h->off_corig; p.off_vorig = h->off_vorig;
@@ -694,6 +752,13 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     }
     // finished lanes OR their set decision bits into the row: rows start out zero
     CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
+    if (h->lean && h->opt_kernel_profile) {
+        if (!d.kprof.p) {
+            if ((rc = d.kprof.reserve(64))) return rc;
+            CU(cudaMemsetAsync(d.kprof.p, 0, 64, st));
+        }
+        p.prof = d.kprof.as<unsigned long long>();
+    }
     if (h->lean) {
         // 32-bit queue arithmetic inside the kernel: at most 2^30 syndromes per launch
         const int64_t kMaxLaunch = 1ll << 30;
@@ -1134,6 +1199,9 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "lean") h->opt_lean = value ? 1 : 0;
+    else if (k == "contiguous_variables") h->opt_cv = value ? 1 : 0;
+    else if (k == "kernel_profile") { h->opt_kernel_profile = value ? 1 : 0; return 0; }
+    else if (k == "max_ctas_per_sm") h->opt_max_ctas = static_cast<int>(value);
     else if (k == "slots") h->opt_slots = static_cast<int>(value);   // accepted for compatibility, unused
     else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
     h->configured = false;
@@ -1313,6 +1381,21 @@ int ldpcb200_selftest_division(int32_t device, int32_t mode, uint64_t n, uint64_
     cudaFree(d);
     if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "selftest: %s", cudaGetErrorString(e));
     for (int k = 0; k < 4; ++k) mismatches[k] = hcount[k];
+    return 0;
+}
+
+int ldpcb200_kernel_profile(ldpcb200_t *h, int32_t dev_slot, int64_t *out8, int32_t reset)
+{
+    if (!h || !out8 || dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad argument");
+    DeviceCtx &d = h->dev[dev_slot];
+    CU(cudaSetDevice(d.device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (d.kprof.p) {
+        CU(cudaMemcpy(v, d.kprof.p, 64, cudaMemcpyDeviceToHost));
+        if (reset) CU(cudaMemset(d.kprof.p, 0, 64));
+    }
+    for (int k = 0; k < 8; ++k) out8[k] = static_cast<int64_t>(v[k]);
     return 0;
 }
 

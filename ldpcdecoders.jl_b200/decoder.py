@@ -93,6 +93,13 @@ class BeliefPropagationDecoder:
         _lib.check(self._lib.ldpcb200_launch_count(self._h, ctypes.byref(out)))
         return out.value
 
+    def kernel_profile(self, reset=True, dev_slot=0):
+        """Per-phase SM cycles of the shared-memory kernel (option kernel_profile=1); see ldpcb200_kernel_profile."""
+        out = (ctypes.c_int64 * 8)()
+        _lib.check(self._lib.ldpcb200_kernel_profile(self._h, dev_slot, out, 1 if reset else 0))
+        names = ("check", "wait_b1", "variable", "flips", "wait_b2", "done_emit", "refill", "warp_iterations")
+        return dict(zip(names, [int(x) for x in out]))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.ldpcb200_destroy(self._h)

@@ -408,7 +408,7 @@ def test_in_library_sharding_over_devices(pkg, oracle, codes, fmt):
             SW, NW = info["syn_words"], info["err_words"]
             pad = np.zeros((SW * 32, B), np.uint8)
             pad[:s] = syn
-            sin = np.packbits(pad.T.reshape(B, SW * 32), axis=1, bitorder="little").view(np.uint32).reshape(B, SW)
+            sin = np.ascontiguousarray(np.packbits(np.ascontiguousarray(pad.T), axis=1, bitorder="little")).view(np.uint32).reshape(B, SW)
             eout = np.zeros((B, NW), dtype=np.uint32)
             conv = np.zeros(B, dtype=np.uint8)
             dec.last_counters = dec.decode_raw(B, np.ascontiguousarray(sin), lib.FMT_PACKED32, SW, eout, lib.FMT_PACKED32, NW, conv, iters)
