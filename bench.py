@@ -3,15 +3,20 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--per P] [--batch B]
   python bench.py --impl reference ...      # the CPU restatement of the reference, all host threads
+  python bench.py --single-process --gpus N # ONE decoder over devices 0..N-1, one 10M-syndrome host batch (strong scaling)
 
 One "step" = one batchdecode! of the whole synthetic batch (default: config C3 of BASELINE.json,
 the [[144,12,12]] gross code, 10M syndromes per GPU, max_iters = 32, reference early-stop
 semantics).  `value` is measured with the packed syndromes already resident in HBM, `e2e` through
-the C-ABI host-buffer call (pinned host BitMatrix in, BitMatrix + success out, copies inside the
-timed region).  Under torchrun every rank decodes its own 10M-syndrome shard (weak scaling,
-inputs keyed by the global syndrome index) and the counters are all-reduced over NCCL.
+the C-ABI host-buffer call (host BitMatrix in, BitMatrix + success out, copies inside the timed
+region; `e2e_by_format` adds pageable buffers and the Matrix{Int} input of the reference's own test).
+Under torchrun every rank decodes its own 10M-syndrome shard (weak scaling, inputs keyed by the
+global syndrome index) and the counters are all-reduced over NCCL.  At N = 1 the line also carries
+short sub-records of the other BASELINE configs at their full batch sizes (C2 per sweep, C4 10M tiled,
+C5 1M streamed).
 """
 import argparse
+import glob
 import json
 import os
 import sys
@@ -27,18 +32,23 @@ import __graft_entry__ as entry  # noqa: E402
 SEED_E = 12345
 METRIC = "decoded syndromes/sec (batchdecode!)"
 UNIT = "syndromes/s"
-# FP64-pipe issue slots per edge-iteration of the reference arithmetic (DESIGN.md "Rooflines"):
-# 10 add/sub/mul + 2 IEEE divisions of D = 8 FP64-pipe instructions each (measured from SASS).
-FP64_SLOTS_PER_EDGE_ITER = 10 + 2 * 8
+# FP64-pipe issue slots per edge-iteration (DESIGN.md "Rooflines").
+#   exact : the reference arithmetic is 10 add/sub/mul + 2 IEEE divisions of D = 8 FP64-pipe instructions each = 26
+#           (the algorithmic model of SURVEY 8(d)); the kernels EXECUTE 21 (products with +-1 and unread values dropped).
+#   minsum: 2 compares + 1 multiply per edge on the check side, 2 additions on the variable side = 5; no divisions.
+FP64_SLOTS = {"exact": {"model": 26, "executed": 21}, "minsum": {"model": 5, "executed": 5}}
 FP64_LANES_PER_SM_CLK = 64
+WORKLOAD_NAMES = {"C1": "Gallager (1000,10,9)", "C2": "d=15 rotated surface X checks", "C3": "[[144,12,12]] gross code H_X",
+                  "C4": "HGP of Gallager(32,4,3) H_X", "C5": "Gallager (100002,6,3)"}
+DEFAULT_PER = {"C1": 0.01, "C2": 0.01, "C3": 0.03, "C4": 0.02, "C5": 0.02}
+DEFAULT_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 10_000_000, "C5": 1_000_000}      # BASELINE.json batch sizes
+DEFAULT_TILE = {"C4": 1_000_000, "C5": 65536}      # syndromes per launch where the batch is tiled / streamed
 
 
 def workload_spec(args, pkg):
     H, per, mi = pkg.codes.config_matrix(args.workload)
-    default_per = {"C1": 0.01, "C2": 0.01, "C3": 0.03, "C4": 0.02, "C5": 0.02}[args.workload]
-    per = args.per if args.per is not None else default_per
-    default_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 65536}[args.workload]
-    B = args.batch if args.batch is not None else default_B
+    per = args.per if args.per is not None else DEFAULT_PER[args.workload]
+    B = args.batch if args.batch is not None else DEFAULT_B[args.workload]
     if args.max_iters is not None:
         mi = args.max_iters
     return H, float(per), int(mi), int(B)
@@ -113,9 +123,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_record(workload, variant, kernel_rev):
+    """The tracked ncu summary (profiles/*.json, written by tools/ncu_summary.py --json on the GPU box) of this
+    workload's dominant kernel, newest round first.  None if no capture is committed -- never a literal."""
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        if d.get("workload") == workload and d.get("variant", "exact") == variant and str(d.get("kernel_rev", "")) == str(kernel_rev):
+            d["file"] = os.path.relpath(path, ROOT)
+            return d
+    return None
+
+
 def cpu_baseline_leg(oracle, H, per, mi, seed, budget_s, nthreads, dense=False):
     """Time the CPU restatement on a bounded sample of the same workload."""
-    probe = 2000
+    probe = 2000 if H.shape[1] < 20000 else 64
     _, syn = oracle.sample(H, per, seed, 0, probe)
     t0 = time.perf_counter()
     oracle.batch_decode(H, per, mi, syn, nthreads=nthreads, dense=dense)
@@ -131,6 +155,18 @@ def cpu_baseline_leg(oracle, H, per, mi, seed, budget_s, nthreads, dense=False):
                 n, "dense s*n (faithful cost)" if dense else "edge-indexed", dt, float(r["iters"].mean()))}
 
 
+def config_dict(args, H, per, mi, B, extra=None):
+    s, n = H.shape
+    d = {"workload": "%s: %s, s=%d n=%d E=%d, per=%g, max_iters=%d, batch=%d syndromes%s, early stop as reference" % (
+        args.workload, WORKLOAD_NAMES[args.workload], s, n, H.nnz, per, mi, B, "" if getattr(args, "single_process", False) else "/GPU"),
+        "per": per, "max_iters": mi, "batch_per_gpu": B, "variant": getattr(args, "variant", "exact"),
+        "l2": "inputs+outputs of one step exceed the 126 MB L2" if B * ((s + 31) // 32 + (n + 31) // 32) * 4 > 130e6
+        else "L2 flushed between steps (256 MB write)"}
+    if extra:
+        d.update(extra)
+    return d
+
+
 def run_reference(args):
     """--impl reference: the restated reference on the host cores (Julia is not installed on
     the box, so oracle/ is the reference arm; PARITY UNPINNED, see oracle/bp_oracle.c)."""
@@ -143,7 +179,7 @@ def run_reference(args):
     H, per, mi, B = workload_spec(args, pkg)
     nthreads = oracle.num_threads()
     # size one step to ~2 s of wall time
-    probe = 4096
+    probe = 4096 if H.shape[1] < 20000 else 64
     _, syn = oracle.sample(H, per, SEED_E, 0, probe)
     oracle.batch_decode(H, per, mi, syn, nthreads=nthreads)          # spins the thread pool up
     t0 = time.perf_counter()
@@ -165,22 +201,11 @@ def run_reference(args):
         n, nthreads, iters_mean)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, H, per, mi, B),
+            "higher_is_better": True, "scaling": "strong" if args.single_process else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, H, per, mi, B),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
-
-
-def config_dict(args, H, per, mi, B):
-    s, n = H.shape
-    return {"workload": "%s: %s, s=%d n=%d E=%d, per=%g, max_iters=%d, batch=%d syndromes/GPU, early stop as reference" % (
-        args.workload, {"C1": "Gallager (1000,10,9)", "C2": "d=15 rotated surface X checks",
-                        "C3": "[[144,12,12]] gross code H_X", "C4": "HGP of Gallager(32,4,3) H_X",
-                        "C5": "Gallager (100002,6,3)"}[args.workload], s, n, H.nnz, per, mi, B),
-            "per": per, "max_iters": mi, "batch_per_gpu": B, "variant": getattr(args, "variant", "exact"),
-            "l2": "inputs+outputs of one step exceed the 126 MB L2" if B * ((s + 31) // 32 + (n + 31) // 32) * 4 > 130e6
-            else "L2 flushed between steps (256 MB write)"}
 
 
 _REAL_STDOUT = None
@@ -202,6 +227,173 @@ def emit(line):
     out.flush()
 
 
+class DeviceRun:
+    """HBM-resident decode loop of one decoder: synthetic syndromes of the whole batch generated on the device
+    (Philox stream keyed by the global syndrome index), decoded in launches of `tile` syndromes."""
+
+    def __init__(self, torch, dev, stream, dec, B, tile=None, first=0, seed=SEED_E):
+        self.torch, self.dev, self.stream, self.dec = torch, dev, stream, dec
+        self.B = int(B)
+        self.tile = int(min(tile or B, B))
+        self.first, self.seed = int(first), seed
+        info = dec.info()
+        self.info = info
+        self.SW, self.NW = info["syn_words"], info["err_words"]
+        self.st = stream.cuda_stream
+        i32 = torch.int32
+        self.synw = torch.empty((self.B, self.SW), dtype=i32, device=dev)
+        # true errors / decoded errors / flags of ONE tile are kept (the batch streams through them)
+        self.truth = torch.empty((self.tile, self.NW), dtype=i32, device=dev)
+        self.errw = torch.empty((self.tile, self.NW), dtype=i32, device=dev)
+        self.conv = torch.empty(self.tile, dtype=torch.uint8, device=dev)
+        self.iters = torch.empty(self.tile, dtype=i32, device=dev)
+        self.ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def sample(self, per):
+        for t0 in range(0, self.B, self.tile):
+            bt = min(self.tile, self.B - t0)
+            self.dec.sample_device(bt, self.first + t0, self.seed, per, self.truth.data_ptr(), self.synw[t0:].data_ptr(), stream=self.st)
+
+    def decode_once(self, ctr=None, B=None):
+        B = self.B if B is None else B
+        for t0 in range(0, B, self.tile):
+            bt = min(self.tile, B - t0)
+            self.dec.decode_device(bt, self.synw[t0:].data_ptr(), self.errw.data_ptr(), self.conv.data_ptr(), self.iters.data_ptr(),
+                                   None, (ctr if ctr is not None else self.ctr).data_ptr(), stream=self.st)
+
+    def timed(self, steps, warmup, flush=None, allreduce=None, barrier=None, warm_one_tile=False):
+        """W warm-ups then `steps` timed decodes of the whole batch; CUDA events on the launching stream.
+        Returns (seconds, summed counters, launches).  warm_one_tile: a warm-up step decodes one launch's worth
+        (long streamed batches: the kernel, clocks and caches are warm after that)."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.ctr.zero_()
+            self.decode_once(B=self.tile if warm_one_tile else None)
+            if allreduce:
+                allreduce(self.ctr)
+        (barrier or torch.cuda.synchronize)()
+        l0 = self.dec.launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        total = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        for a, b in evs:
+            if flush is not None:
+                flush.fill_(1)
+            self.ctr.zero_()
+            a.record(self.stream)
+            self.decode_once()
+            if allreduce:
+                allreduce(self.ctr)            # the path's only collective: 4 int64 counters
+            b.record(self.stream)
+            total += self.ctr
+        (barrier or torch.cuda.synchronize)()
+        secs = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        return secs, total.cpu().numpy(), self.dec.launch_count() - l0
+
+    def exact_match_frac_last_tile(self, per):
+        """Exact-match fraction of the LAST tile decoded (its true errors are regenerated from the same stream)."""
+        torch = self.torch
+        score = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        t0 = (self.B - 1) // self.tile * self.tile
+        bt = self.B - t0
+        self.dec.sample_device(bt, self.first + t0, self.seed, per, self.truth.data_ptr(), self.synw[t0:].data_ptr(), stream=self.st)
+        self.dec.score_device(bt, self.truth.data_ptr(), self.errw.data_ptr(), self.synw[t0:].data_ptr(), score.data_ptr(), stream=self.st)
+        torch.cuda.synchronize()
+        return float(score[0].item()) / bt
+
+
+def roofline_of(info, variant, E, SW, NW, B_per_step_gpu, units_per_step_gpu, step_s, clk_mhz, peaks, peaks_src, ncu):
+    """Roofline object of the dominant kernel (this rank's share, this rank's time)."""
+    io_bytes = B_per_step_gpu * (SW * 4 + NW * 4 + 1 + 4)
+    alg_bytes = units_per_step_gpu * 4.0 * E * 8.0 + io_bytes
+    traffic = None
+    if ncu and ncu.get("dram_bytes_read") is not None and ncu.get("syndromes"):
+        # DRAM bytes of the profiled launch, scaled to this step's batch (both are linear in the batch)
+        traffic = (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) * B_per_step_gpu / float(ncu["syndromes"])
+    if info["family"] == 1:
+        slots = FP64_SLOTS[variant]
+        peak = info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12
+        ach = units_per_step_gpu * E * slots["model"] / step_s / 1e12
+        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "frac_model_%d" % slots["model"]: ach / peak,
+                "frac_executed_%d" % slots["executed"]: units_per_step_gpu * E * slots["executed"] / step_s / 1e12 / peak,
+                "traffic": traffic,
+                "note": "shared-memory-resident kernel: bounded by the FP64 pipe, not HBM or tensor cores. achieved = (syndrome-iterations) x E x %d "
+                        "FP64-pipe issue slots per edge-iteration of the %s arithmetic per step / CUDA-event time; frac_executed counts the %d the kernel "
+                        "issues (comparable with ncu's sm__pipe_fp64_cycles_active); peak = %d SMs x 64 FP64 lanes/clk x median SM clock under load "
+                        "(%.0f MHz); one FLOP = one FP64 lane-instruction" % (
+                            slots["model"], "reference" if variant == "exact" else "min-sum", slots["executed"], info["sm_count"], clk_mhz),
+                "ncu": ncu,
+                "hbm_model": {"achieved_GBps": alg_bytes / step_s / 1e9, "peak_GBps": peaks["hbm_gbs"], "peak_source": peaks_src,
+                              "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"],
+                              "note": "4*E*8 B per syndrome-iteration if messages lived in HBM (they live in shared memory) + packed I/O"}}
+    else:
+        roof = {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+                "algorithmic_bytes_per_step": alg_bytes,
+                "note": "algorithmic bytes = 4*E*8 per syndrome-iteration + packed I/O; peak = %s copy bandwidth; message store %d MB per GPU" % (
+                    peaks_src, info["message_bytes"] >> 20),
+                "ncu": ncu}
+    return roof
+
+
+def sub_record(pkg, torch, dev, stream, name, per, B, tile, steps, warmup, peaks, peaks_src, clk_mhz, oracle=None, cpu_budget=3.0,
+               variant="exact", **opts):
+    """One BASELINE config next to the headline: HBM-resident throughput at its full batch size, roofline, CPU baseline."""
+    H, _, mi = pkg.codes.config_matrix(name)
+    dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[dev.index], variant=variant, **opts)
+    run = DeviceRun(torch, dev, stream, dec, B, tile)
+    run.sample(per)
+    secs, c, launches = run.timed(steps, warmup, warm_one_tile=run.tile < B)
+    info = run.info
+    rec = {"workload": "%s: %s, s=%d n=%d E=%d, per=%g, max_iters=%d, batch=%d%s" % (
+        name, WORKLOAD_NAMES[name], H.shape[0], H.shape[1], H.nnz, per, mi, B,
+        "" if run.tile >= B else " streamed from HBM in launches of %d" % run.tile),
+        "per": per, "value": float(c[0]) / secs, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
+        "mean_iters": float(c[2]) / max(float(c[0]), 1.0), "converged_frac": float(c[1]) / max(float(c[0]), 1.0),
+        "syndrome_iterations_per_s": float(c[2]) / secs, "gpu_launches": int(launches),
+        "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "message_bytes", "prefetch_distance", "kernel_rev")}}
+    rec["roofline"] = roofline_of(info, variant, H.nnz, run.SW, run.NW, B, float(c[2]) / steps, secs / steps, clk_mhz, peaks, peaks_src,
+                                  ncu_record(name, variant, info["kernel_rev"]))
+    if oracle is not None:
+        rec["cpu_baseline"] = cpu_baseline_leg(oracle, H, per, mi, SEED_E, cpu_budget, oracle.num_threads())
+    dec.close()
+    del run
+    torch.cuda.empty_cache()
+    return rec
+
+
+def host_bitmatrix(torch, dev, synw, s, B, pinned):
+    """Host BitMatrix (bit c*s + r of a little-endian stream) of the packed device rows synw[:B]."""
+    nb = (B * s + 63) // 64 * 8
+    bit_ar = torch.arange(s, device=dev, dtype=torch.int64)
+    weights = (2 ** torch.arange(8, device=dev, dtype=torch.int32)).to(torch.uint8)
+    acc = torch.zeros(nb * 8, dtype=torch.uint8, device=dev)
+    sl = 1 << 19
+    for b0 in range(0, B, sl):
+        w = synw[b0:min(b0 + sl, B)].to(torch.int64) & 0xFFFFFFFF
+        bits = ((w[:, bit_ar // 32] >> (bit_ar % 32)) & 1).to(torch.uint8)       # [rows, s]
+        acc[b0 * s:(b0 + bits.shape[0]) * s] = bits.reshape(-1)
+        del w, bits
+    d_bits = (acc.view(-1, 8) * weights).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+    del acc
+    h = torch.empty(nb, dtype=torch.uint8, pin_memory=pinned)
+    h.copy_(d_bits)
+    torch.cuda.synchronize()
+    return h
+
+
+def e2e_leg(dec, B, np_in, fmt_in, ld_in, np_out, fmt_out, ld_out, np_conv, steps, barrier, warm=2):
+    for _ in range(warm):
+        dec.decode_raw(B, np_in, fmt_in, ld_in, np_out, fmt_out, ld_out, np_conv)
+    barrier()
+    l0 = dec.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dec.decode_raw(B, np_in, fmt_in, ld_in, np_out, fmt_out, ld_out, np_conv)
+    barrier()
+    return time.perf_counter() - t0, dec.launch_count() - l0
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
@@ -212,10 +404,13 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--per", type=float, default=None)
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--tile", type=int, default=None, help="syndromes per launch (C4 / C5 stream their batch through HBM in tiles)")
     ap.add_argument("--max-iters", type=int, default=None, dest="max_iters")
-    ap.add_argument("--no-sweep", action="store_true", help="skip the extra per / forced-iteration points")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the extra operating points and the C2/C4/C5 sub-records")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-process", action="store_true", dest="single_process",
+                    help="ONE decoder on devices 0..N-1 (in-library sharding, std::thread per device), one host batch: strong scaling")
     ap.add_argument("--family", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1)
@@ -237,12 +432,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    if args.single_process:
+        if world > 1 and rank != 0:          # launched under torchrun: rank 0 alone owns all devices
+            return
+        return run_single_process(args, torch)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     entry.build()
     pkg = entry.load_package()
+    lib = pkg._lib
     H, per, mi, B = workload_spec(args, pkg)
     s, n = H.shape
     E = H.nnz
@@ -260,14 +460,12 @@ def main():
     if args.kernel_profile:
         opts["kernel_profile"] = 1
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant=args.variant, **opts)
-    info = dec.info()
-    SW, NW = info["syn_words"], info["err_words"]
     # a non-default torch stream: its handle is non-NULL, so the library launches on exactly the
     # stream the torch CUDA events are recorded on (NULL would mean "the handle's own stream")
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    st = stream.cuda_stream
-    assert st != 0
+    assert stream.cuda_stream != 0
+    tile = args.tile if args.tile is not None else DEFAULT_TILE.get(args.workload)
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,343 +473,177 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
     # ---- synthetic inputs, resident in HBM; shard r owns global syndromes [r*B, (r+1)*B)
-    truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
-    synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
-    errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
-    conv = torch.empty(B, dtype=torch.uint8, device=dev)
-    iters = torch.empty(B, dtype=torch.int32, device=dev)
-    ctr = torch.zeros(4, dtype=torch.int64, device=dev)
-    score = torch.zeros(2, dtype=torch.int64, device=dev)
+    run = DeviceRun(torch, dev, stream, dec, B, tile, first=rank * B)
+    info = run.info
+    SW, NW = run.SW, run.NW
     flush = None
     if B * (SW + NW) * 4 <= 130e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def sample(per_):
-        dec.sample_device(B, rank * B, SEED_E, per_, truth.data_ptr(), synw.data_ptr(), stream=st)
-
-    def timed_run(steps, warmup):
-        """W warm-ups then `steps` timed decodes; returns (seconds of the slowest rank, counters, launches)."""
-        for _ in range(warmup):
-            ctr.zero_()
-            dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), None, ctr.data_ptr(), stream=st)
-            if world > 1:
-                dist.all_reduce(ctr)
-        barrier()
-        l0 = dec.launch_count()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        total_ctr = torch.zeros(4, dtype=torch.int64, device=dev)
-        for a, b in evs:
-            if flush is not None:
-                flush.fill_(1)
-            ctr.zero_()
-            a.record(stream)
-            dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), None, ctr.data_ptr(), stream=st)
-            if world > 1:
-                dist.all_reduce(ctr)          # the path's only collective: 4 int64 counters
-            b.record(stream)
-            total_ctr += ctr
-        barrier()
-        secs = sum(a.elapsed_time(b) for a, b in evs) / 1e3
-        t = torch.tensor([secs], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), total_ctr.cpu().numpy(), dec.launch_count() - l0
-
-    sample(per)
+    run.sample(per)
+    run.timed(0, args.warmup, flush, allreduce, barrier)
     sampler = ClockSampler(local)
-    # clocks are sampled during the timed region only (warm-up runs before start())
-    for _ in range(args.warmup):
-        dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), None, ctr.data_ptr(), stream=st)
-    barrier()
-    sampler.start()
-    secs, c, launches = timed_run(args.steps, 0)
+    sampler.start()                               # clocks are sampled during the timed region only
+    secs, c, launches = run.timed(args.steps, 0, flush, allreduce, barrier)
     clocks = sampler.stop()
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
     n_dec_all = float(c[0])                       # all ranks (counters were all-reduced), all steps
     value = n_dec_all / secs
     mean_iters = float(c[2]) / max(float(c[0]), 1.0)
     conv_frac = float(c[1]) / max(float(c[0]), 1.0)
-    # logical scoring of the last step (not timed): exact-match fraction
-    score.zero_()
-    dec.score_device(B, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), score.data_ptr(), stream=st)
-    torch.cuda.synchronize()
-    exact_frac = float(score[0].item()) / B
+    exact_frac = run.exact_match_frac_last_tile(per)
 
     # ---- roofline of the dominant kernel (this rank's share, this rank's time)
     peaks, peaks_src = measured_peaks()
-    units_per_step_gpu = float(c[2]) / args.steps / world           # (syndrome, iteration) pairs per launch per GPU
+    units_per_step_gpu = float(c[2]) / args.steps / world           # (syndrome, iteration) pairs per step per GPU
     step_s = secs / args.steps
     clk_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    io_bytes = B * (SW * 4 + NW * 4 + 1 + 4)
-    alg_bytes = units_per_step_gpu * 4.0 * E * 8.0 + io_bytes
-    if info["family"] == 1:
-        fp64_ops = units_per_step_gpu * E * FP64_SLOTS_PER_EDGE_ITER
-        peak = info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12
-        roof = {"bound": "fp64", "achieved": fp64_ops / step_s / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": fp64_ops / step_s / 1e12 / peak, "traffic": None,
-                "note": "shared-memory-resident kernel: bounded by the FP64 pipe, not HBM or tensor cores. "
-                        "achieved = (syndrome-iterations) x E x %d FP64-pipe issue slots (10 add/sub/mul + 2 IEEE divisions x 8) per launch / CUDA-event time; "
-                        "peak = %d SMs x 64 FP64 lanes/clk x median SM clock under load (%.0f MHz); one FLOP = one FP64 lane-instruction" % (
-                            FP64_SLOTS_PER_EDGE_ITER, info["sm_count"], clk_mhz),
-                "ncu": ({"launch": "2 000 000-syndrome launch of this workload under ncu --set full (not a bench value)",
-                         "smsp__issue_active_pct": 57.1, "sm__pipe_fp64_cycles_active_pct": 42.4,
-                         "fp64_share_of_issued_warp_instructions_pct": 37.4, "executed_fp64_slots_per_edge_iteration": 21,
-                         "dram_bytes_read": 64074240, "dram_bytes_write": 2648832,
-                         "previous_12_warp_shape": {"smsp__issue_active_pct": 61.2, "sm__pipe_fp64_cycles_active_pct": 41.8,
-                                                    "source": "profiles/r1_persistent_kernel_c3_mode0_12warps_ncu_full.txt"},
-                         "source": "profiles/r1_persistent_kernel_c3_mode0_ncu_full.txt"}
-                        if args.workload == "C3" and args.variant == "exact" else None),
-                "hbm_model": {"achieved_GBps": alg_bytes / step_s / 1e9, "peak_GBps": peaks["hbm_gbs"], "peak_source": peaks_src,
-                              "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"],
-                              "note": "4*E*8 B per syndrome-iteration if messages lived in HBM (they live in shared memory) + packed I/O"}}
-    else:
-        roof = {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                "note": "algorithmic bytes = 4*E*8 per syndrome-iteration + packed I/O; peak %s copy bandwidth; the message store (%d MB) is sized to stay L2-resident, so >1.0 is possible" % (
-                    peaks_src, info["message_bytes"] >> 20)}
+    roof = roofline_of(info, args.variant, E, SW, NW, B, units_per_step_gpu, step_s, clk_mhz, peaks, peaks_src,
+                       ncu_record(args.workload, args.variant, info["kernel_rev"]))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(args, H, per, mi, B),
+            "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, H, per, mi, B, {"tile": run.tile} if run.tile < B else None),
             "mean_iters": mean_iters, "converged_frac": conv_frac, "exact_match_frac": exact_frac,
             "syndrome_iterations_per_s": float(c[2]) / secs,
             "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
             "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "smem_bytes", "slots",
                                             "message_bytes", "prefetch_distance", "kernel_rev")}}
-
     if args.kernel_profile:
         kp = dec.kernel_profile()
         wi = max(kp["warp_iterations"], 1)
         line["kernel_profile_cycles_per_warp_iteration"] = {k: round(v / wi, 1) for k, v in kp.items() if k != "warp_iterations"}
 
-    # ---- end to end through the host-buffer C-ABI call (Julia BitMatrix in / out), pinned memory
+    # ---- end to end through the host-buffer C-ABI call
     if not args.no_e2e:
-        lib = pkg._lib
-        nb_in = (B * s + 63) // 64 * 8
-        nb_out = (B * n + 63) // 64 * 8
-        h_in = torch.empty(nb_in, dtype=torch.uint8, pin_memory=True)
-        h_out = torch.empty(nb_out, dtype=torch.uint8, pin_memory=True)
-        h_conv = torch.empty(B, dtype=torch.uint8, pin_memory=True)
-        # host BitMatrix of this rank's syndromes (built once, untimed): bit c*s + r of the stream
-        bit_ar = torch.arange(s, device=dev, dtype=torch.int64)
-        weights = (2 ** torch.arange(8, device=dev, dtype=torch.int32)).to(torch.uint8)
-        acc = torch.zeros(nb_in * 8, dtype=torch.uint8, device=dev)
-        sl = 1 << 19
-        for b0 in range(0, B, sl):
-            w = synw[b0:b0 + sl].to(torch.int64) & 0xFFFFFFFF
-            bits = ((w[:, bit_ar // 32] >> (bit_ar % 32)) & 1).to(torch.uint8)       # [rows, s]
-            acc[b0 * s:(b0 + bits.shape[0]) * s] = bits.reshape(-1)
-            del w, bits
-        d_bits = (acc.view(-1, 8) * weights).sum(dim=1, dtype=torch.int32).to(torch.uint8)
-        del acc
-        h_in.copy_(d_bits)
-        del d_bits
-        torch.cuda.synchronize()
-        np_in, np_out, np_conv = h_in.numpy(), h_out.numpy(), h_conv.numpy()
+        Be = int(min(B, 10_000_000))
         e2e_steps = max(2, min(args.steps, 5))
-        for _ in range(2):
-            dec.decode_raw(B, np_in, lib.FMT_BITS, 0, np_out, lib.FMT_BITS, 0, np_conv)
-        barrier()
-        l0 = dec.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            cnt = dec.decode_raw(B, np_in, lib.FMT_BITS, 0, np_out, lib.FMT_BITS, 0, np_conv)
-        barrier()
-        dt = time.perf_counter() - t0
+        conv_dev_count = None
+        if world == 1:          # converged count of the same syndromes from the device-resident path
+            cchk = torch.zeros(4, dtype=torch.int64, device=dev)
+            run.decode_once(cchk, Be)
+            torch.cuda.synchronize()
+            conv_dev_count = int(cchk[1].item())
+        h_in = host_bitmatrix(torch, dev, run.synw, s, Be, pinned=True)
+        nb_out = (Be * n + 63) // 64 * 8
+        h_out = torch.empty(nb_out, dtype=torch.uint8, pin_memory=True)
+        h_conv = torch.empty(Be, dtype=torch.uint8, pin_memory=True)
+        np_in, np_out, np_conv = h_in.numpy(), h_out.numpy(), h_conv.numpy()
+        dt, nl = e2e_leg(dec, Be, np_in, lib.FMT_BITS, 0, np_out, lib.FMT_BITS, 0, np_conv, e2e_steps, barrier)
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        # outputs of the host path must equal the device-resident path's
-        got_conv = int(np_conv.sum())
-        line["e2e"] = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(nb_in),
-                       "d2h_bytes_per_step": int(nb_out + B), "steps": e2e_steps,
-                       "api": "ldpcb200_decode_batch(FMT_BITS in/out, pinned host buffers), wall clock around the blocking call",
-                       "converged_check": got_conv == int(c[1] / args.steps / world) if world == 1 else None,
-                       "gpu_launches": int(dec.launch_count() - l0)}
+        line["e2e"] = {"value": world * Be * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel()),
+                       "d2h_bytes_per_step": int(nb_out + Be), "steps": e2e_steps, "batch_per_gpu": Be,
+                       "api": "ldpcb200_decode_batch(FMT_BITS in/out = Julia BitMatrix, pinned host buffers), wall clock around the blocking call",
+                       "converged_check": (int(np_conv.sum()) == conv_dev_count) if conv_dev_count is not None else None,
+                       "gpu_launches": int(nl)}
+        if world == 1 and not args.no_sweep and args.workload in ("C2", "C3"):
+            # the same call with the buffers a Julia caller really has: pageable arrays, and the Matrix{Int} syndromes of
+            # the reference's own test (test/test_bp_decoder.jl:24-26: batchdecode!(bpd, syndromes::Matrix{Int}, zero(errors)::BitMatrix))
+            table = [{"in": "BitMatrix", "out": "BitMatrix", "host_memory": "pinned", "batch": Be, "value": line["e2e"]["value"],
+                      "h2d_bytes": int(h_in.numel()), "d2h_bytes": int(nb_out + Be)}]
+            pg_in = np.array(np_in, copy=True)            # ordinary (pageable) numpy memory
+            pg_out = np.zeros(nb_out, dtype=np.uint8)
+            pg_conv = np.zeros(Be, dtype=np.uint8)
+            dt, _ = e2e_leg(dec, Be, pg_in, lib.FMT_BITS, 0, pg_out, lib.FMT_BITS, 0, pg_conv, e2e_steps, barrier)
+            ok = bool(np.array_equal(pg_out, np_out) and np.array_equal(pg_conv, np_conv))
+            table.append({"in": "BitMatrix", "out": "BitMatrix", "host_memory": "pageable", "batch": Be, "value": Be * e2e_steps / dt,
+                          "h2d_bytes": int(pg_in.size), "d2h_bytes": int(nb_out + Be), "same_outputs_as_pinned": ok})
+            Bi = int(min(Be, 2_000_000))                  # Matrix{Int}: 8 bytes per syndrome bit -> a 2M-column sample (1.2 GB)
+            st2 = max(2, e2e_steps // 2)
+            bits = np.unpackbits(np_in[: (Bi * s + 7) // 8], bitorder="little")[: Bi * s]
+            syn_i64 = np.asfortranarray(bits.reshape(Bi, s).T.astype(np.int64))
+            out_b = np.zeros((Bi * n + 63) // 64 * 8, dtype=np.uint8)
+            cv_b = np.zeros(Bi, dtype=np.uint8)
+            dt, _ = e2e_leg(dec, Bi, syn_i64, lib.FMT_I64, s, out_b, lib.FMT_BITS, 0, cv_b, st2, barrier, warm=1)
+            nb = Bi * n // 8
+            table.append({"in": "Matrix{Int}", "out": "BitMatrix", "host_memory": "pageable", "batch": Bi,
+                          "value": Bi * st2 / dt, "h2d_bytes": int(syn_i64.nbytes), "d2h_bytes": int(out_b.size + Bi),
+                          "same_outputs_as_pinned": bool(np.array_equal(out_b[:nb], np_out[:nb]) and np.array_equal(cv_b, np_conv[:Bi])),
+                          "note": "the call of test/test_bp_decoder.jl:24-26; 8 bytes of PCIe traffic per syndrome bit"})
+            syn_u8 = np.asfortranarray(bits.reshape(Bi, s).T.astype(np.uint8))
+            out_u8 = np.zeros((n, Bi), dtype=np.uint8, order="F")
+            dt, _ = e2e_leg(dec, Bi, syn_u8, lib.FMT_U8, s, out_u8, lib.FMT_U8, n, cv_b, st2, barrier, warm=1)
+            table.append({"in": "Matrix{Bool}", "out": "Matrix{Bool}", "host_memory": "pageable", "batch": Bi,
+                          "value": Bi * st2 / dt, "h2d_bytes": int(syn_u8.nbytes), "d2h_bytes": int(out_u8.nbytes + Bi)})
+            line["e2e_by_format"] = table
+            del pg_in, pg_out, syn_i64, syn_u8, out_u8, out_b, bits
+        del h_in, h_out, h_conv
 
-    # ---- extra operating points (not the headline): per sweep and forced max_iters
-    if not args.no_sweep and args.workload in ("C2", "C3"):
+    # ---- extra operating points of the headline code (not the headline): per sweep, forced max_iters, min-sum
+    if world == 1 and not args.no_sweep and args.workload in ("C2", "C3") and args.variant == "exact":
         sweep = []
-        pts = {"C3": [0.001, 0.01, 0.03, 0.1], "C2": [0.001, 0.01, 0.03, 0.1]}[args.workload]
-        for p_ in pts:
+        for p_ in ([0.001, 0.01, 0.03, 0.1] if args.workload == "C3" else [0.001, 0.003, 0.01, 0.03, 0.1]):
             d2 = pkg.BeliefPropagationDecoder(H, p_, mi, devices=[local], **opts)
-            dec_saved = dec
-            dec = d2
-            sample(p_)
-            secs2, c2, _ = timed_run(3, 1)
+            r2 = DeviceRun(torch, dev, stream, d2, B)
+            r2.sample(p_)
+            secs2, c2, _ = r2.timed(3, 1, flush)
             sweep.append({"per": p_, "value": float(c2[0]) / secs2, "mean_iters": float(c2[2]) / float(c2[0]),
                           "converged_frac": float(c2[1]) / float(c2[0]), "syndrome_iterations_per_s": float(c2[2]) / secs2})
             d2.close()
-            dec = dec_saved
+            del r2
         # forced iterations: its own decoder, so that the library configures for that mode (early_stop = 0 before the
-        # first decode selects the 12-warp shape; the early-stop runs use 8 warps)
+        # first decode)
         d2 = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], early_stop=0, **opts)
-        dec_saved = dec
-        dec = d2
-        sample(per)
-        secs2, c2, _ = timed_run(2, 1)
+        r2 = DeviceRun(torch, dev, stream, d2, B)
+        r2.sample(per)
+        secs2, c2, _ = r2.timed(2, 1, flush)
         d2.close()
-        dec = dec_saved
+        del r2
+        peak = info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12
         sweep.append({"per": per, "forced_iters": mi, "value": float(c2[0]) / secs2, "mean_iters": float(c2[2]) / float(c2[0]),
                       "syndrome_iterations_per_s": float(c2[2]) / secs2,
-                      "fp64_frac": float(c2[2]) / 2 / world * E * FP64_SLOTS_PER_EDGE_ITER / (secs2 / 2) / 1e12 /
-                      (info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12)})
+                      "fp64_frac_model_26": float(c2[2]) * E * 26 / secs2 / 1e12 / peak,
+                      "fp64_frac_executed_21": float(c2[2]) * E * 21 / secs2 / 1e12 / peak})
         line["sweep"] = sweep
-
-    # ---- sum-product vs min-sum (BASELINE.json config 3): the normalised min-sum kernels on the same
-    # syndromes; no reference equivalent, so it is reported by quality, not parity
-    if world == 1 and not args.no_sweep and args.variant == "exact" and args.workload in ("C2", "C3"):
-        errw_sp = errw.clone()
+        # sum-product vs min-sum (BASELINE.json config 3): the normalised min-sum kernels on the same syndromes; no
+        # reference equivalent, so it is reported by quality, not parity
+        errw_sp = run.errw.clone()
         dms = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant="minsum")
-        dec_saved = dec
-        dec = dms
-        secs2, c2_, _ = timed_run(3, 2)
-        score.zero_()
-        dms.score_device(B, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), score.data_ptr(), stream=st)
-        torch.cuda.synchronize()
-        differ = int((errw != errw_sp).any(dim=1).sum().item())
+        rms = DeviceRun(torch, dev, stream, dms, B)
+        rms.sample(per)
+        secs2, c2_, _ = rms.timed(3, 2, flush)
+        ms_info = rms.info
+        differ = int((rms.errw != errw_sp).any(dim=1).sum().item()) if run.tile >= B else None
+        ms_roof = roofline_of(ms_info, "minsum", E, SW, NW, B, float(c2_[2]) / 3, secs2 / 3, clk_mhz, peaks, peaks_src,
+                              ncu_record(args.workload, "minsum", ms_info["kernel_rev"]))
         line["minsum"] = {"value": float(c2_[0]) / secs2, "unit": UNIT, "per": per, "scale": 0.875,
                           "mean_iters": float(c2_[2]) / float(c2_[0]), "converged_frac": float(c2_[1]) / float(c2_[0]),
-                          "exact_match_frac": float(score[0].item()) / B,
-                          "decisions_differ_from_sum_product_frac": differ / B,
-                          "note": "FP64 log-likelihood-ratio min-sum, same schedule/early stop; sum-product exact_match_frac is the line's own"}
-        dec = dec_saved
+                          "exact_match_frac": rms.exact_match_frac_last_tile(per),
+                          "decisions_differ_from_sum_product_frac": differ / B if differ is not None else None,
+                          "roofline": {k: ms_roof[k] for k in ms_roof if k not in ("note", "hbm_model")},
+                          "note": "FP64 log-likelihood-ratio min-sum, same schedule/early stop; sum-product exact_match_frac is the line's own; "
+                                  "5 FP64-pipe slots per edge-iteration (no divisions): the kernel is issue/shared-memory bound, not FP64 bound"}
         dms.close()
-        del errw_sp
-
-    # ---- config C2 of BASELINE.json next to the headline (1 M syndromes, per sweep), N = 1 only
-    if world == 1 and not args.no_sweep and args.workload == "C3":
-        H2, _, mi2 = pkg.codes.config_matrix("C2")
-        B2 = 1_000_000
-        c2 = []
-        for p_ in (0.001, 0.01, 0.03, 0.1):
-            d2 = pkg.BeliefPropagationDecoder(H2, p_, mi2, devices=[local])
-            i2 = d2.info()
-            t2 = torch.empty((B2, i2["err_words"]), dtype=torch.int32, device=dev)
-            s2 = torch.empty((B2, i2["syn_words"]), dtype=torch.int32, device=dev)
-            e2 = torch.empty((B2, i2["err_words"]), dtype=torch.int32, device=dev)
-            cv2 = torch.empty(B2, dtype=torch.uint8, device=dev)
-            c4 = torch.zeros(4, dtype=torch.int64, device=dev)
-            d2.sample_device(B2, 0, SEED_E, p_, t2.data_ptr(), s2.data_ptr(), stream=st)
-            for _ in range(3):
-                d2.decode_device(B2, s2.data_ptr(), e2.data_ptr(), cv2.data_ptr(), None, None, None, stream=st)
-            torch.cuda.synchronize()
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 5
-            ea.record(stream)
-            for _ in range(reps):
-                if flush is not None:
-                    pass
-                d2.decode_device(B2, s2.data_ptr(), e2.data_ptr(), cv2.data_ptr(), None, None, c4.data_ptr(), stream=st)
-            eb.record(stream)
-            torch.cuda.synchronize()
-            secs2 = ea.elapsed_time(eb) / 1e3
-            cc = c4.cpu().numpy()
-            c2.append({"per": p_, "value": float(cc[0]) / secs2, "mean_iters": float(cc[2]) / float(cc[0]),
-                       "converged_frac": float(cc[1]) / float(cc[0]), "syndrome_iterations_per_s": float(cc[2]) / secs2,
-                       "fp64_frac": float(cc[2]) / secs2 * H2.nnz * FP64_SLOTS_PER_EDGE_ITER / 1e12 /
-                       (info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12)})
-            d2.close()
-            del t2, s2, e2, cv2
-        line["config_C2_surface_d15_1M"] = c2
+        del errw_sp, rms
 
     # ---- BASELINE.json config 4 is "the BP stage of BP+OSD": the whole BP -> OSD-0 pipeline on the same syndromes
     # (ldpcb200_decode_device with posterior ratios, then ldpcb200_osd0_device on the unconverged ones)
     if world == 1 and not args.no_sweep and args.workload == "C4" and args.variant == "exact":
-        Bo = int(min(B, 131072))
-        ratio = torch.empty((Bo, n), dtype=torch.float64, device=dev)
-        stats = torch.zeros(8, dtype=torch.int64, device=dev)
-        sc_bp = torch.zeros(2, dtype=torch.int64, device=dev)
-        sc_osd = torch.zeros(2, dtype=torch.int64, device=dev)
+        line["bposd_osd0"] = bposd_record(args, pkg, torch, dev, stream, dec, run, H, per, mi, n, SW, NW)
 
-        def bp_stage():
-            dec.decode_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), ratio.data_ptr(),
-                              ctr.data_ptr(), stream=st)
-
-        def osd_stage():
-            dec.osd0_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), ratio.data_ptr(), stats.data_ptr(), stream=st)
-
-        dec.set_option("ratio_last_only", 1)
-        for _ in range(2):
-            bp_stage()
-            osd_stage()
-        torch.cuda.synchronize()
-        reps = 3
-        t_bp = t_osd = 0.0
-        stats.zero_()
-        ctr.zero_()
-        for _ in range(reps):
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record(stream)
-            bp_stage()
-            e1.record(stream)
-            if _ == 0:
-                dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_bp.data_ptr(), stream=st)
-                torch.cuda.synchronize()
-            e1b = torch.cuda.Event(enable_timing=True)
-            e1b.record(stream)
-            osd_stage()
-            e2.record(stream)
-            torch.cuda.synchronize()
-            t_bp += e0.elapsed_time(e1) / 1e3
-            t_osd += e1b.elapsed_time(e2) / 1e3
-        dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_osd.data_ptr(), stream=st)
-        torch.cuda.synchronize()
-        so = stats.cpu().numpy()
-        nproc = float(so[0]) / reps
-        if os.environ.get("LDPCB200_OSD_PROFILE"):     # one extra pass with the kernel's per-phase cycle counters on
-            dec.set_option("osd_profile", 1)
-            stats.zero_()
-            bp_stage()
-            osd_stage()
-            torch.cuda.synchronize()
-            sp_ = stats.cpu().numpy()
-            sys.stderr.write("osd phases (SM cycles per syndrome): sort %.0f build %.0f search %.0f update %.0f solve %.0f\n" %
-                             tuple(float(sp_[k]) / max(float(sp_[0]), 1.0) for k in (3, 4, 5, 6, 7)))
-            dec.set_option("osd_profile", 0)
-        bposd = {"batch": Bo, "per": per, "value": Bo * reps / (t_bp + t_osd), "unit": UNIT,
-                 "bp_stage_syndromes_per_s": Bo * reps / t_bp,
-                 "osd_stage_syndromes_per_s": float(so[0]) / t_osd if t_osd > 0 else None,
-                 "osd_stage_ms": t_osd / reps * 1e3, "bp_stage_ms": t_bp / reps * 1e3,
-                 "unconverged_frac": nproc / Bo,
-                 "mean_pivots": float(so[1]) / max(float(so[0]), 1.0), "mean_columns_visited": float(so[2]) / max(float(so[0]), 1.0),
-                 "bp_exact_match_frac": float(sc_bp[0].item()) / Bo, "bp_syndrome_satisfied_frac": float(sc_bp[1].item()) / Bo,
-                 "bposd_exact_match_frac": float(sc_osd[0].item()) / Bo,
-                 "bposd_syndrome_satisfied_frac": float(sc_osd[1].item()) / Bo,
-                 "note": "device-resident; the BP stage writes posterior ratios only in iteration max_iters (ratio_last_only)"}
-        if not args.no_e2e:
-            # the reference-facing call: host arrays in, host arrays out (ldpcb200_bposd_decode_batch)
-            import time as _t
-            syn_t = torch.empty((Bo, SW), dtype=torch.int32, pin_memory=True)      # pinned, like the headline e2e leg
-            syn_t.copy_(synw[:Bo])
-            err_t = torch.zeros((Bo, NW), dtype=torch.int32, pin_memory=True)
-            conv_t = torch.zeros(Bo, dtype=torch.uint8, pin_memory=True)
-            torch.cuda.synchronize()
-            syn_h, err_h, conv_h = syn_t.numpy().view(np.uint32), err_t.numpy().view(np.uint32), conv_t.numpy()
-            dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
-            t0 = _t.perf_counter()
-            for _ in range(reps):
-                dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
-            dt = _t.perf_counter() - t0
-            bposd["e2e"] = {"value": Bo * reps / dt, "unit": UNIT, "h2d_bytes_per_step": int(Bo * SW * 4),
-                            "d2h_bytes_per_step": int(Bo * (NW * 4 + 1)),
-                            "api": "ldpcb200_bposd_decode_batch(FMT_PACKED32 in/out, pinned host buffers), wall clock"}
-        if not args.no_cpu:
-            import time as _t
-            oracle = entry.load_oracle()
-            nth = oracle.num_threads()
-            Kc = 8 * nth
-            _, syn_c = oracle.sample(H, per, SEED_E, 0, Kc)
-            oracle.bposd_decode(H, per, mi, syn_c[:, :nth], nthreads=nth)
-            t0 = _t.perf_counter()
-            oracle.bposd_decode(H, per, mi, syn_c, nthreads=nth)
-            dt = _t.perf_counter() - t0
-            bposd["cpu_baseline"] = {"value": Kc / dt, "unit": UNIT, "cores": nth, "kind": "port",
-                                     "sample": "first %d syndromes of the same stream, BP + restated OSD-0 (bit-packed rows)" % Kc}
-        line["bposd_osd0"] = bposd
-        dec.set_option("ratio_last_only", 0)
-        del ratio
+    # ---- the other BASELINE configs next to the headline at their full batch sizes (N = 1, default workload only)
+    if world == 1 and not args.no_sweep and args.workload == "C3" and args.variant == "exact":
+        oracle = None if args.no_cpu else entry.load_oracle()
+        del run
+        run = None
+        torch.cuda.empty_cache()
+        c2rec = []
+        for p_ in (0.001, 0.003, 0.01, 0.03, 0.1):
+            c2rec.append(sub_record(pkg, torch, dev, stream, "C2", p_, DEFAULT_B["C2"], None, 5, 3, peaks, peaks_src, clk_mhz,
+                                    oracle=oracle if p_ == 0.01 else None, cpu_budget=2.0))
+        line["config_C2_surface_d15_1M"] = c2rec
+        line["config_C4_hgp1600_10M"] = sub_record(pkg, torch, dev, stream, "C4", DEFAULT_PER["C4"], DEFAULT_B["C4"], DEFAULT_TILE["C4"], 2, 3,
+                                                   peaks, peaks_src, clk_mhz, oracle=oracle, cpu_budget=3.0)
+        line["config_C5_gallager100k_1M"] = sub_record(pkg, torch, dev, stream, "C5", DEFAULT_PER["C5"], DEFAULT_B["C5"], DEFAULT_TILE["C5"], 1, 3,
+                                                       peaks, peaks_src, clk_mhz, oracle=oracle, cpu_budget=3.0)
 
     # ---- CPU baseline next to it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -626,6 +658,177 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bposd_record(args, pkg, torch, dev, stream, dec, run, H, per, mi, n, SW, NW):
+    st = stream.cuda_stream
+    Bo = int(min(run.tile, 131072))
+    synw, errw, conv, iters, ctr, truth = run.synw, run.errw, run.conv, run.iters, run.ctr, run.truth
+    ratio = torch.empty((Bo, n), dtype=torch.float64, device=dev)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    sc_bp = torch.zeros(2, dtype=torch.int64, device=dev)
+    sc_osd = torch.zeros(2, dtype=torch.int64, device=dev)
+    dec.sample_device(Bo, run.first, SEED_E, per, truth.data_ptr(), synw.data_ptr(), stream=st)
+
+    def bp_stage():
+        dec.decode_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), iters.data_ptr(), ratio.data_ptr(),
+                          ctr.data_ptr(), stream=st)
+
+    def osd_stage():
+        dec.osd0_device(Bo, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), ratio.data_ptr(), stats.data_ptr(), stream=st)
+
+    dec.set_option("ratio_last_only", 1)
+    for _ in range(2):
+        bp_stage()
+        osd_stage()
+    torch.cuda.synchronize()
+    reps = 3
+    t_bp = t_osd = 0.0
+    stats.zero_()
+    ctr.zero_()
+    for rep in range(reps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        bp_stage()
+        e1.record(stream)
+        if rep == 0:
+            dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_bp.data_ptr(), stream=st)
+            torch.cuda.synchronize()
+        e1b = torch.cuda.Event(enable_timing=True)
+        e1b.record(stream)
+        osd_stage()
+        e2.record(stream)
+        torch.cuda.synchronize()
+        t_bp += e0.elapsed_time(e1) / 1e3
+        t_osd += e1b.elapsed_time(e2) / 1e3
+    dec.score_device(Bo, truth.data_ptr(), errw.data_ptr(), synw.data_ptr(), sc_osd.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    so = stats.cpu().numpy()
+    nproc = float(so[0]) / reps
+    if os.environ.get("LDPCB200_OSD_PROFILE"):     # one extra pass with the kernel's per-phase cycle counters on
+        dec.set_option("osd_profile", 1)
+        stats.zero_()
+        bp_stage()
+        osd_stage()
+        torch.cuda.synchronize()
+        sp_ = stats.cpu().numpy()
+        sys.stderr.write("osd phases (SM cycles per syndrome): sort %.0f build %.0f search %.0f update %.0f solve %.0f\n" %
+                         tuple(float(sp_[k]) / max(float(sp_[0]), 1.0) for k in (3, 4, 5, 6, 7)))
+        dec.set_option("osd_profile", 0)
+    bposd = {"batch": Bo, "per": per, "value": Bo * reps / (t_bp + t_osd), "unit": UNIT,
+             "bp_stage_syndromes_per_s": Bo * reps / t_bp,
+             "osd_stage_syndromes_per_s": float(so[0]) / t_osd if t_osd > 0 else None,
+             "osd_stage_ms": t_osd / reps * 1e3, "bp_stage_ms": t_bp / reps * 1e3,
+             "unconverged_frac": nproc / Bo,
+             "mean_pivots": float(so[1]) / max(float(so[0]), 1.0), "mean_columns_visited": float(so[2]) / max(float(so[0]), 1.0),
+             "bp_exact_match_frac": float(sc_bp[0].item()) / Bo, "bp_syndrome_satisfied_frac": float(sc_bp[1].item()) / Bo,
+             "bposd_exact_match_frac": float(sc_osd[0].item()) / Bo,
+             "bposd_syndrome_satisfied_frac": float(sc_osd[1].item()) / Bo,
+             "note": "device-resident; the BP stage writes posterior ratios only in iteration max_iters (ratio_last_only)"}
+    if not args.no_e2e:
+        # the reference-facing call: host arrays in, host arrays out (ldpcb200_bposd_decode_batch)
+        syn_t = torch.empty((Bo, SW), dtype=torch.int32, pin_memory=True)
+        syn_t.copy_(synw[:Bo])
+        err_t = torch.zeros((Bo, NW), dtype=torch.int32, pin_memory=True)
+        conv_t = torch.zeros(Bo, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        syn_h, err_h, conv_h = syn_t.numpy().view(np.uint32), err_t.numpy().view(np.uint32), conv_t.numpy()
+        dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dec.bposd_raw(Bo, syn_h, pkg._lib.FMT_PACKED32, SW, err_h, pkg._lib.FMT_PACKED32, NW, conv_h)
+        dt = time.perf_counter() - t0
+        bposd["e2e"] = {"value": Bo * reps / dt, "unit": UNIT, "h2d_bytes_per_step": int(Bo * SW * 4),
+                        "d2h_bytes_per_step": int(Bo * (NW * 4 + 1)),
+                        "api": "ldpcb200_bposd_decode_batch(FMT_PACKED32 in/out, pinned host buffers), wall clock"}
+    if not args.no_cpu:
+        oracle = entry.load_oracle()
+        nth = oracle.num_threads()
+        Kc = 8 * nth
+        _, syn_c = oracle.sample(H, per, SEED_E, 0, Kc)
+        oracle.bposd_decode(H, per, mi, syn_c[:, :nth], nthreads=nth)
+        t0 = time.perf_counter()
+        oracle.bposd_decode(H, per, mi, syn_c, nthreads=nth)
+        dt = time.perf_counter() - t0
+        bposd["cpu_baseline"] = {"value": Kc / dt, "unit": UNIT, "cores": nth, "kind": "port",
+                                 "sample": "first %d syndromes of the same stream, BP + restated OSD-0 (bit-packed rows)" % Kc}
+    dec.set_option("ratio_last_only", 0)
+    del ratio
+    return bposd
+
+
+def run_single_process(args, torch):
+    """ONE decoder handle over devices 0..N-1: the call a Julia user makes with `devices = 0:N-1`.  The library splits
+    the host batch into contiguous column ranges (std::thread per device, chunked double-buffered copies) and sums the
+    counters (ncclAllReduce over its own communicators when NCCL is available).  The batch is FIXED (BASELINE config 3:
+    one 10M-syndrome batch at 1/2/4/8 GPUs): strong scaling."""
+    N = int(args.gpus)
+    if torch.cuda.device_count() < N:
+        raise SystemExit("--single-process --gpus %d needs %d visible devices (found %d)" % (N, N, torch.cuda.device_count()))
+    entry.build()
+    pkg = entry.load_package()
+    lib = pkg._lib
+    H, per, mi, B = workload_spec(args, pkg)
+    s, n = H.shape
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    # reference run on device 0 alone, device-resident: converged count / iterations the sharded call must reproduce
+    d0 = pkg.BeliefPropagationDecoder(H, per, mi, devices=[0], variant=args.variant)
+    run = DeviceRun(torch, dev, stream, d0, B)
+    run.sample(per)
+    run.ctr.zero_()
+    run.decode_once()
+    torch.cuda.synchronize()
+    want = run.ctr.cpu().numpy().copy()
+    h_in = host_bitmatrix(torch, dev, run.synw, s, B, pinned=True)
+    d0.close()
+    del run
+    torch.cuda.empty_cache()
+    dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=list(range(N)), variant=args.variant)
+    info = dec.info()
+    nb_out = (B * n + 63) // 64 * 8
+    h_out = torch.empty(nb_out, dtype=torch.uint8, pin_memory=True)
+    h_conv = torch.empty(B, dtype=torch.uint8, pin_memory=True)
+    np_in, np_out, np_conv = h_in.numpy(), h_out.numpy(), h_conv.numpy()
+
+    def sync_all():
+        for k in range(N):
+            torch.cuda.synchronize(k)
+
+    cnt = None
+    for _ in range(max(args.warmup, 3)):
+        cnt = dec.decode_raw(B, np_in, lib.FMT_BITS, 0, np_out, lib.FMT_BITS, 0, np_conv)
+    sync_all()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = dec.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cnt = dec.decode_raw(B, np_in, lib.FMT_BITS, 0, np_out, lib.FMT_BITS, 0, np_conv)
+    sync_all()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = dec.launch_count() - l0
+    value = B * args.steps / dt
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "mode": "single-process: one ldpcb200 handle over %d devices" % N,
+            "config": config_dict(args, H, per, mi, B, {"host_memory": "pinned", "format": "BitMatrix in / BitMatrix out"}),
+            "mean_iters": float(cnt[2]) / max(float(cnt[0]), 1.0), "converged_frac": float(cnt[1]) / max(float(cnt[0]), 1.0),
+            "counters_match_single_device_run": bool(int(cnt[0]) == int(want[0]) and int(cnt[1]) == int(want[1]) and int(cnt[2]) == int(want[2])),
+            "converged_check": bool(int(np_conv.sum()) == int(want[1])),
+            "counters_via_nccl": bool(info["counters_via_nccl"]),
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel()), "d2h_bytes_per_step": int(nb_out + B),
+                    "api": "ldpcb200_decode_batch on a %d-device handle (FMT_BITS in/out, pinned host buffers); `value` IS this end-to-end number: "
+                           "the timed region is the blocking host call" % N},
+            "roofline": None,
+            "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "kernel_rev", "ndev")},
+            "note": "wall clock around the blocking call on a fixed host batch; the device-resident weak-scaling figure is the default mode"}
+    dec.close()
+    emit(line)
 
 
 if __name__ == "__main__":

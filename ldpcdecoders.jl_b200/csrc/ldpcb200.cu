@@ -5,6 +5,8 @@
 // /root/reference/src/decoders/belief_propagation.jl:38-67,121-188,220-231.
 // No CPU fallback exists in this file: every decode runs the CUDA kernels or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>          // types and prototypes only: libnccl.so.2 is bound with dlopen when a handle spans several devices
 
 #include <algorithm>
 #include <atomic>
@@ -12,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -46,6 +49,41 @@ int fail(int code, const char *fmt, ...)
             return fail(e_ == cudaErrorMemoryAllocation ? LDPCB200_ENOMEM : LDPCB200_ECUDA,        \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// ---- NCCL, bound at run time (one ncclAllReduce of the counters per batch).  The library
+// has no link-time dependency on NCCL: a single-device handle never touches it, and inside a process that already
+// carries an NCCL (PyTorch bundles one) dlopen by SONAME binds to that copy.
+struct NcclApi {
+    bool tried = false, ok = false;
+    std::string why;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+bool nccl_load()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl.tried) return g_nccl.ok;
+    g_nccl.tried = true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { g_nccl.why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+    auto sym = [&](const char *name) { void *p = dlsym(lib, name); if (!p) g_nccl.why = std::string("missing symbol ") + name; return p; };
+    g_nccl.CommInitAll = reinterpret_cast<decltype(&ncclCommInitAll)>(sym("ncclCommInitAll"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(&ncclCommDestroy)>(sym("ncclCommDestroy"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(&ncclAllReduce)>(sym("ncclAllReduce"));
+    g_nccl.GroupStart = reinterpret_cast<decltype(&ncclGroupStart)>(sym("ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<decltype(&ncclGroupEnd)>(sym("ncclGroupEnd"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(&ncclGetErrorString)>(sym("ncclGetErrorString"));
+    g_nccl.ok = g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
+    return g_nccl.ok;
+}
 
 struct DevBuf {
     void *p = nullptr;
@@ -110,9 +148,16 @@ struct DeviceCtx {
         cudaStream_t stream = nullptr;
         DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio;
         DevBuf osd_list, osd_ctl;            // OSD-0: unconverged list, {count, queue}
+        // pageable caller memory is staged through pinned blocks so that the copies stay asynchronous: the chunk's
+        // input is gathered into pin_in by the host thread while the GPU works on the previous chunk; outputs land in
+        // pin_out and are handed to the caller (`pending`) when this set comes round again
+        PinnedBuf pin_in, pin_out;
+        size_t pin_out_used = 0;
+        struct Pending { void *dst; const void *src; size_t bytes; };
+        std::vector<Pending> pending;
     } set[2];
     cudaEvent_t decode_done = nullptr;
-    DevBuf counters, scratch, osd_stats, kprof;
+    DevBuf counters, scratch, osd_stats, kprof, ctr_sum;
     DevBuf tiny;            // small-batch host calls: one device block ...
     PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
@@ -139,6 +184,7 @@ struct ldpcb200 {
     int tables_cv_warps = 0;             // layout the device copies of `tables` currently have
     bool tables_dirty = false;           // host blob rebuilt, device copies stale
     int opt_cv = 1;                      // bp_smem_kernel: contiguous variable ownership where the code allows it
+    int opt_stage_pageable = 1;          // host batches: stage pageable caller memory through pinned blocks (0: copy it directly)
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
     int64_t opt_chunk = 0;
@@ -159,6 +205,12 @@ struct ldpcb200 {
     bp::KernelParams kp_proto{};
     std::vector<DeviceCtx> dev;
     std::atomic<long long> launches{0};
+    // counters of a multi-device handle: ncclAllReduce over the handle's own communicators (one per device) when NCCL
+    // is available and the devices are distinct; otherwise (or with option "nccl" = 0) the host adds the per-device values
+    int opt_nccl = 1;
+    int nccl_state = 0;                 // 0 not tried, 1 communicators ready, -1 unavailable (see nccl_why)
+    std::string nccl_why;
+    std::vector<ncclComm_t> comms;
 };
 
 namespace {
@@ -454,11 +506,12 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof}) b->release();
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
         for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
             b->release();
+    for (auto &S : d.set) { S.pin_in.release(); S.pin_out.release(); }
     if (d.decode_done) cudaEventDestroy(d.decode_done);
     if (d.set[1].stream) cudaStreamDestroy(d.set[1].stream);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -949,6 +1002,33 @@ int decode_host_tiny(ldpcb200 *h, DeviceCtx &d, int64_t B, const void *syndromes
     return 0;
 }
 
+// memcpy between caller memory and a pinned staging block, split over a few host threads when it is large
+void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const size_t kSlice = 8u << 20;
+    if (bytes < 2 * kSlice) { memcpy(dst, src, bytes); return; }
+    const int nt = static_cast<int>(std::min<size_t>(4, bytes / kSlice));
+    const size_t per = (bytes / nt + 63) / 64 * 64;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const size_t o = per * t, len = std::min(per, bytes - std::min(bytes, o));
+        if (len) th.emplace_back([=] { memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &t : th) t.join();
+}
+
+// Ordinary (pageable) host memory?  cudaMemcpyAsync from/to it is staged by the driver and blocks the calling thread,
+// which serialises the two-stream pipeline below; pinned or registered memory (cudaHostAlloc, cudaHostRegister,
+// CUDA.jl's pinned arrays) is copied directly.
+bool is_pageable(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 // One device's share [b0, b0+Bd) of a host batch, processed in chunks.
 int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t Btot, const void *syndromes,
                       int syn_fmt, int64_t syn_ld, void *errors, int err_fmt, int64_t err_ld, uint8_t *converged,
@@ -974,8 +1054,15 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     // (the OSD pipeline keeps n posterior ratios per syndrome on the device: its chunks are bounded by 2 GB, and two
     // chunks per call are enough to overlap the copies -- every chunk pays a BP tail and an OSD tail)
     const double budget = osd ? 2048.0 * 1048576.0 : std::min(std::max(256.0 * 1048576.0, two_waves), 2048.0 * 1048576.0);
+    // pageable caller buffers are staged through pinned memory by this thread: more, smaller chunks keep the part of
+    // that host-side copying that cannot overlap GPU work (first chunk in, last chunk out) small
+    const bool pg_in = h->opt_stage_pageable && is_pageable(syndromes);
+    const bool pg_out = h->opt_stage_pageable && is_pageable(errors);
+    const bool pg_conv = h->opt_stage_pageable && is_pageable(converged), pg_iters = h->opt_stage_pageable && is_pageable(iters),
+               pg_ratio = h->opt_stage_pageable && is_pageable(ratio);
+    const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : 4);
     int64_t CH = h->opt_chunk > 0 ? h->opt_chunk
-                                  : std::max<int64_t>({(Bd + (osd ? 1 : 3)) / (osd ? 2 : 4), 32768, 2 * static_cast<int64_t>(h->slots)});
+                                  : std::max<int64_t>({(Bd + nchunk_target - 1) / nchunk_target, 32768, 2 * static_cast<int64_t>(h->slots)});
     CH = std::min<int64_t>(CH, static_cast<int64_t>(budget / std::max(per_syn, 1.0)));
     CH = std::max<int64_t>(32, (CH + 31) / 32 * 32);
     int rc;
@@ -992,8 +1079,41 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         DeviceCtx::StageSet &S = d.set[chunk_no & 1];
         cudaStream_t st = S.stream;
         CU(cudaStreamSynchronize(st));                    // the chunk that used this set two steps ago has landed
+        for (const auto &pd : S.pending) par_memcpy(pd.dst, pd.src, pd.bytes);      // ... hand its staged outputs to the caller
+        S.pending.clear();
+        S.pin_out_used = 0;
         const int64_t Bc = std::min(CH, Bd - c0);
         const int64_t g0 = b0 + c0;                       // first global column of this chunk
+        // copies between the caller's memory and the device, through the pinned staging blocks when that memory is pageable
+        auto h2d = [&](void *dst_dev, const void *src_host, size_t bytes, bool staged) -> int {
+            if (staged) {
+                int r_ = S.pin_in.reserve(bytes);
+                if (r_) return r_;
+                par_memcpy(S.pin_in.p, src_host, bytes);
+                src_host = S.pin_in.p;
+            }
+            CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+            return 0;
+        };
+        auto d2h = [&](void *dst_host, const void *src_dev, size_t bytes, bool staged) -> int {
+            if (staged) {
+                unsigned char *q = static_cast<unsigned char *>(S.pin_out.p) + S.pin_out_used;
+                S.pin_out_used += (bytes + 255) / 256 * 256;
+                S.pending.push_back({dst_host, q, bytes});
+                dst_host = q;
+            }
+            CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+            return 0;
+        };
+        {   // one pinned output block per chunk, sized before the first copy is issued (it must not move afterwards)
+            size_t need_out = 0;
+            auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+            if (pg_out) need_out += up(fmt_bytes(err_fmt, n, err_ld, Bc, h->NW) + 8);
+            if (pg_conv) need_out += up(static_cast<size_t>(Bc));
+            if (pg_iters) need_out += up(static_cast<size_t>(Bc) * 4);
+            if (pg_ratio) need_out += up(static_cast<size_t>(Bc) * n * 8);
+            if (need_out && (rc = S.pin_out.reserve(need_out))) return rc;
+        }
         if ((rc = S.syn_words.reserve(static_cast<size_t>(Bc) * h->SW * 4))) return rc;
         if ((rc = S.err_words.reserve(static_cast<size_t>(Bc) * h->NW * 4))) return rc;
         if ((rc = S.conv.reserve(static_cast<size_t>(Bc)))) return rc;
@@ -1002,27 +1122,26 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         // ---- syndromes -> device -> packed rows
         uint32_t *syn_words = S.syn_words.as<uint32_t>();
         if (syn_fmt == LDPCB200_FMT_PACKED32) {
-            CU(cudaMemcpyAsync(syn_words, static_cast<const uint32_t *>(syndromes) + g0 * h->SW,
-                               static_cast<size_t>(Bc) * h->SW * 4, cudaMemcpyHostToDevice, st));
+            if ((rc = h2d(syn_words, static_cast<const uint32_t *>(syndromes) + g0 * h->SW, static_cast<size_t>(Bc) * h->SW * 4, pg_in))) return rc;
         } else if (syn_fmt == LDPCB200_FMT_BITS) {
             const size_t w0 = static_cast<size_t>(g0 * s / 32);           // g0 is a multiple of 32
             const size_t nw = static_cast<size_t>((Bc * s + 31) / 32);
             if ((rc = S.raw_in.reserve(nw * 4))) return rc;
-            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const uint32_t *>(syndromes) + w0, nw * 4, cudaMemcpyHostToDevice, st));
+            if ((rc = h2d(S.raw_in.p, static_cast<const uint32_t *>(syndromes) + w0, nw * 4, pg_in))) return rc;
             bp::pack_bits<<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<uint32_t>(), static_cast<long long>(nw),
                                                                             static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
         } else if (syn_fmt == LDPCB200_FMT_U8) {
             const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
             if ((rc = S.raw_in.reserve(bytes))) return rc;
-            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const uint8_t *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            if ((rc = h2d(S.raw_in.p, static_cast<const uint8_t *>(syndromes) + g0 * syn_ld, bytes, pg_in))) return rc;
             bp::pack_elems<uint8_t><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<uint8_t>(), syn_ld,
                                                                                      static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
         } else if (syn_fmt == LDPCB200_FMT_I64) {
             const size_t bytes = fmt_bytes(syn_fmt, s, syn_ld, Bc, h->SW);
             if ((rc = S.raw_in.reserve(bytes))) return rc;
-            CU(cudaMemcpyAsync(S.raw_in.p, static_cast<const long long *>(syndromes) + g0 * syn_ld, bytes, cudaMemcpyHostToDevice, st));
+            if ((rc = h2d(S.raw_in.p, static_cast<const long long *>(syndromes) + g0 * syn_ld, bytes, pg_in))) return rc;
             bp::pack_elems<long long><<<grid_for(Bc * h->SW, d.sm_count), 256, 0, st>>>(S.raw_in.as<long long>(), syn_ld,
                                                                                        static_cast<int>(s), h->SW, Bc, syn_words);
             h->launches++;
@@ -1049,8 +1168,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         // ---- packed rows -> caller's format -> host
         const uint32_t *ew = S.err_words.as<uint32_t>();
         if (err_fmt == LDPCB200_FMT_PACKED32) {
-            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + g0 * h->NW, ew, static_cast<size_t>(Bc) * h->NW * 4,
-                               cudaMemcpyDeviceToHost, st));
+            if ((rc = d2h(static_cast<uint32_t *>(errors) + g0 * h->NW, ew, static_cast<size_t>(Bc) * h->NW * 4, pg_out))) return rc;
         } else if (err_fmt == LDPCB200_FMT_BITS) {
             const size_t w0 = static_cast<size_t>(g0 * n / 32);
             const size_t nw = static_cast<size_t>((Bc * n + 31) / 32);
@@ -1058,7 +1176,9 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
             bp::unpack_bits<<<grid_for(static_cast<long long>(nw), d.sm_count), 256, 0, st>>>(
                 ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<uint32_t>(), static_cast<long long>(nw));
             h->launches++;
-            CU(cudaMemcpyAsync(static_cast<uint32_t *>(errors) + w0, S.raw_out.p, nw * 4, cudaMemcpyDeviceToHost, st));
+            // (the last word of a chunk may hold bits of the next chunk's first column only when Bc*n is not a multiple
+            //  of 32, i.e. in the final chunk of the batch: chunk boundaries are multiples of 32 columns)
+            if ((rc = d2h(static_cast<uint32_t *>(errors) + w0, S.raw_out.p, nw * 4, pg_out))) return rc;
         } else if (err_fmt == LDPCB200_FMT_U8 || err_fmt == LDPCB200_FMT_I64 || err_fmt == LDPCB200_FMT_F64) {
             const size_t bytes = fmt_bytes(err_fmt, n, err_ld, Bc, h->NW);
             if ((rc = S.raw_out.reserve(bytes))) return rc;
@@ -1073,8 +1193,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
             h->launches++;
             const size_t esz = err_fmt == LDPCB200_FMT_U8 ? 1 : 8;
             if (err_ld == n) {
-                CU(cudaMemcpyAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, S.raw_out.p, bytes,
-                                   cudaMemcpyDeviceToHost, st));
+                if ((rc = d2h(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, S.raw_out.p, bytes, pg_out))) return rc;
             } else {   // strided destination: only the n rows of each column belong to the caller
                 CU(cudaMemcpy2DAsync(static_cast<uint8_t *>(errors) + static_cast<size_t>(g0) * err_ld * esz, err_ld * esz,
                                      S.raw_out.p, err_ld * esz, n * esz, Bc, cudaMemcpyDeviceToHost, st));
@@ -1082,12 +1201,20 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         } else {
             return fail(LDPCB200_EINVAL, "unsupported error format %d", err_fmt);
         }
-        CU(cudaMemcpyAsync(converged + g0, S.conv.p, static_cast<size_t>(Bc), cudaMemcpyDeviceToHost, st));
-        if (iters) CU(cudaMemcpyAsync(iters + g0, S.iters.p, static_cast<size_t>(Bc) * 4, cudaMemcpyDeviceToHost, st));
-        if (ratio) CU(cudaMemcpyAsync(ratio + g0 * n, S.ratio.p, static_cast<size_t>(Bc) * n * 8, cudaMemcpyDeviceToHost, st));
+        if ((rc = d2h(converged + g0, S.conv.p, static_cast<size_t>(Bc), pg_conv))) return rc;
+        if (iters && (rc = d2h(iters + g0, S.iters.p, static_cast<size_t>(Bc) * 4, pg_iters))) return rc;
+        if (ratio && (rc = d2h(ratio + g0 * n, S.ratio.p, static_cast<size_t>(Bc) * n * 8, pg_ratio))) return rc;
     }
-    CU(cudaStreamSynchronize(d.set[0].stream));
-    CU(cudaStreamSynchronize(d.set[1].stream));
+    {   // drain both sets, the older chunk first, and hand the staged outputs to the caller
+        const int last = static_cast<int>((chunk_no + 1) & 1), prev = static_cast<int>(chunk_no & 1);   // chunk_no = chunks issued
+        for (int k : {prev, last}) {
+            DeviceCtx::StageSet &S = d.set[k];
+            CU(cudaStreamSynchronize(S.stream));
+            for (const auto &pd : S.pending) par_memcpy(pd.dst, pd.src, pd.bytes);
+            S.pending.clear();
+            S.pin_out_used = 0;
+        }
+    }
     cudaStream_t st = d.set[0].stream;
     unsigned long long hc[LDPCB200_NUM_COUNTERS];
     CU(cudaMemcpyAsync(hc, d.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -1099,6 +1226,55 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         CU(cudaStreamSynchronize(st));
         for (int k = 0; k < LDPCB200_NUM_OSD_STATS; ++k) osd_stats_out[k] = static_cast<int64_t>(ho[k]);
     }
+    return 0;
+}
+
+// Communicators for the handle's device set (lazy: the first multi-device batch that asks for counters).
+void nccl_prepare(ldpcb200 *h)
+{
+    if (h->nccl_state != 0) return;
+    h->nccl_state = -1;
+    const int nd = static_cast<int>(h->dev.size());
+    if (nd < 2 || !h->opt_nccl) { h->nccl_why = nd < 2 ? "single device" : "disabled by option"; return; }
+    std::vector<int> devs;
+    for (const DeviceCtx &d : h->dev) {
+        if (std::find(devs.begin(), devs.end(), d.device) != devs.end()) { h->nccl_why = "a device is listed twice (NCCL needs distinct devices)"; return; }
+        devs.push_back(d.device);
+    }
+    if (!nccl_load()) { h->nccl_why = g_nccl.why; return; }
+    h->comms.assign(nd, nullptr);
+    ncclResult_t r = g_nccl.CommInitAll(h->comms.data(), nd, devs.data());
+    if (r != ncclSuccess) { h->nccl_why = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r); h->comms.clear(); return; }
+    h->nccl_state = 1;
+}
+
+// Sum the per-device counter blocks (d.counters, 4 x uint64, complete on d.set[0].stream) over all devices of the
+// handle with one grouped ncclAllReduce; the result of device 0 goes to `out`.
+int nccl_sum_counters(ldpcb200 *h, int64_t *out)
+{
+    const int nd = static_cast<int>(h->dev.size());
+    for (int k = 0; k < nd; ++k) {
+        DeviceCtx &d = h->dev[k];
+        CU(cudaSetDevice(d.device));
+        int rc = d.ctr_sum.reserve(LDPCB200_NUM_COUNTERS * 8);
+        if (rc) return rc;
+    }
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int k = 0; k < nd && r == ncclSuccess; ++k) {
+        DeviceCtx &d = h->dev[k];
+        r = g_nccl.AllReduce(d.counters.p, d.ctr_sum.p, LDPCB200_NUM_COUNTERS, ncclUint64, ncclSum, h->comms[k], d.set[0].stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) return fail(LDPCB200_ECUDA, "ncclAllReduce of the counters: %s", g_nccl.GetErrorString(r));
+    unsigned long long hc[LDPCB200_NUM_COUNTERS];
+    for (int k = 0; k < nd; ++k) {
+        DeviceCtx &d = h->dev[k];
+        CU(cudaSetDevice(d.device));
+        if (k == 0) CU(cudaMemcpyAsync(hc, d.ctr_sum.p, sizeof(hc), cudaMemcpyDeviceToHost, d.set[0].stream));
+        CU(cudaStreamSynchronize(d.set[0].stream));
+    }
+    for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) out[c] = static_cast<int64_t>(hc[c]);
     return 0;
 }
 
@@ -1180,6 +1356,9 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
 int ldpcb200_destroy(ldpcb200_t *h)
 {
     if (!h) return 0;
+    if (h->nccl_state == 1)
+        for (ncclComm_t cm : h->comms)
+            if (cm) g_nccl.CommDestroy(cm);
     for (DeviceCtx &d : h->dev) destroy_device(d);
     delete h;
     return 0;
@@ -1190,6 +1369,8 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (!h || !key) return fail(LDPCB200_EINVAL, "null handle or key");
     const std::string k(key);
     if (k == "small_batch") { h->opt_small_batch = value; return 0; }
+    if (k == "stage_pageable") { h->opt_stage_pageable = value ? 1 : 0; return 0; }
+    if (k == "nccl") { h->opt_nccl = value ? 1 : 0; return 0; }      // before the first multi-device batch
     if (k == "osd_profile") { h->opt_osd_profile = value ? 1 : 0; return 0; }
     if (k == "ratio_last_only") { h->opt_ratio_last_only = value ? 1 : 0; return 0; }
     if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration
@@ -1228,7 +1409,8 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
     out->kernel_mode = h->mode;
     out->prefetch_distance = h->kp_proto.pd;
     out->kernel_rev = h->lean ? 2 : 1;
-    out->counters_via_nccl = 0;
+    nccl_prepare(h);
+    out->counters_via_nccl = h->nccl_state == 1 ? 1 : 0;
     return 0;
 }
 
@@ -1290,9 +1472,24 @@ static int decode_batch_impl(ldpcb200_t *h, int64_t B, const void *syndromes, in
     }
     for (int k = 0; k < nd; ++k)
         if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
-    if (counters)
-        for (int k = 0; k < nd; ++k)
-            for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) counters[c] += ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS + c];
+    if (counters) {
+        bool summed = false;
+        if (nd > 1) {
+            nccl_prepare(h);
+            // every device must have decoded a share (its counter block then holds this call's values; a batch too
+            // small for that is summed on the host)
+            bool all_shares = true;
+            for (int k = 0; k < nd; ++k) all_shares &= lo[k + 1] > lo[k];
+            if (h->nccl_state == 1 && all_shares) {
+                int rc2 = nccl_sum_counters(h, counters);
+                if (rc2) return rc2;
+                summed = true;
+            }
+        }
+        if (!summed)
+            for (int k = 0; k < nd; ++k)
+                for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) counters[c] += ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS + c];
+    }
     if (osd_stats)
         for (int k = 0; k < nd; ++k)
             for (int c = 0; c < LDPCB200_NUM_OSD_STATS; ++c) osd_stats[c] += ost[static_cast<size_t>(k) * LDPCB200_NUM_OSD_STATS + c];

@@ -758,3 +758,28 @@ def test_bposd_syndromes_outside_the_column_space(pkg, oracle, codes):
         bad = np.nonzero((g["errors"] != ref["errors"]).any(axis=0))[0]
         assert bad.size == 0, (n, wr, wc, per, mi, bad[:10])
         assert np.array_equal(g["converged"], ref["converged"]) and g["stats"][1] == int(ref["pivots"].sum())
+
+
+def test_pinned_and_pageable_host_memory_agree(pkg, oracle, codes):
+    """The host-batch call stages pageable caller memory through pinned blocks and copies pinned (or registered)
+    memory directly; both must give the oracle's answer, chunk by chunk (several chunks: chunk = 4096)."""
+    H, _, mi = codes.config_matrix("C3")
+    s, n = H.shape
+    B = 50_000
+    _, syn = oracle.sample(H, 0.05, 4242, 0, B)
+    ref = oracle.batch_decode(H, 0.05, mi, syn, nthreads=oracle.num_threads())
+    lib = pkg._lib
+    for stage in (1, 0):
+        dec = pkg.BeliefPropagationDecoder(H, 0.05, mi, chunk=4096, stage_pageable=stage)
+        for pinned in (False, True):
+            t_in = torch.from_numpy(np.ascontiguousarray(syn.T.astype(np.uint8)))          # [B][s] bytes == column-major s x B
+            t_out = torch.zeros((B, n), dtype=torch.uint8)
+            t_conv = torch.zeros(B, dtype=torch.uint8)
+            t_it = torch.zeros(B, dtype=torch.int32)
+            if pinned:
+                t_in, t_out, t_conv, t_it = (x.pin_memory() for x in (t_in, t_out, t_conv, t_it))
+            cnt = dec.decode_raw(B, t_in.numpy(), lib.FMT_U8, s, t_out.numpy(), lib.FMT_U8, n, t_conv.numpy(), t_it.numpy())
+            assert np.array_equal(t_out.numpy().T, ref["errors"]), (stage, pinned)
+            assert np.array_equal(t_conv.numpy().astype(bool), ref["converged"]) and np.array_equal(t_it.numpy(), ref["iters"])
+            assert cnt[0] == B and cnt[1] == int(ref["converged"].sum())
+        dec.close()
