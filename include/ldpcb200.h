@@ -70,7 +70,8 @@ typedef struct {
     int64_t message_bytes;      /* device bytes of the message store per device (family GLOBAL) */
     int32_t kernel_mode;        /* 0: all in shared memory, 1: messages in HBM/L2, 2: messages + state + tables in HBM/L2 */
     int32_t prefetch_distance;  /* cp.async ring depth of modes 1/2 (0 = messages read directly) */
-    int32_t kernel_rev;         /* 2: round-2 shared-memory kernel (bp_smem.cuh), 1: the general persistent kernel (bp_kernel.cuh) */
+    int32_t kernel_rev;         /* 2: round-2 shared-memory kernel (bp_smem.cuh); 3: the same kernel with two teams per CTA taking turns
+                                   in the check pass (option "dual" = 1); 1: the general persistent kernel (bp_kernel.cuh, option "lean" = 0) */
     int32_t counters_via_nccl;  /* 1: the per-device counters of a multi-device handle are summed with ncclAllReduce */
 } ldpcb200_info_t;
 

@@ -73,6 +73,7 @@ struct KernelParams {
     int tables_bytes;             // multiple of 16
     int off_colptr, off_ve, off_vflip;   // byte offsets inside the blob (rowptr at 0)
     int off_corig, off_vorig;            // u16 original ids of the kernels' check / variable order (if permuted)
+    int group_stride;                    // bp_smem_kernel<DUAL>: byte distance between the two teams' groups of arrays (0: one group)
     int cv_cpw, cv_stride;               // bp_smem_kernel, contiguous variable ownership: variables per warp (0 = interleaved), bytes per warp in the ve table
     int perm_c, perm_v;                  // node order differs from the caller's (degree-sorted)
     Segments seg;

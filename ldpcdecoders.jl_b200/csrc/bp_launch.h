@@ -23,7 +23,9 @@ BP_DECLARE_MODE(0, 0, 1) BP_DECLARE_MODE(1, 0, 1) BP_DECLARE_MODE(2, 0, 1)
 // shared-memory-resident kernel of round 2 (bp_smem.cuh), one translation unit per variant V
 #define BP_DECLARE_SMEM(V)                                                                                  \
     cudaError_t smem_kernel_attrs_##V(int shape, int eb64, int smem_bytes, int threads, int *blocks_per_sm); \
-    void smem_kernel_launch_##V(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
+    void smem_kernel_launch_##V(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p); \
+    cudaError_t smem_dual_attrs_##V(int eb64, int smem_bytes, int threads, int *blocks_per_sm);                  \
+    void smem_dual_launch_##V(int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
 BP_DECLARE_SMEM(0) BP_DECLARE_SMEM(1)
 #undef BP_DECLARE_SMEM
 

@@ -70,21 +70,52 @@ __device__ __forceinline__ void var_group(uint32_t ml, uint32_t ta, double p0, b
         for (int k = 0; k < D; ++k) st_msg(ml + off[v * D + k], o[v][k]);
 }
 
-template <int MAXT, int MINB, bool EB64, bool PROF = false>
+template <int MAXT, int MINB, bool EB64, bool PROF = false, bool DUAL = false>
 __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_constant__ KernelParams p)
 {
     using ebits_t = typename std::conditional<EB64, unsigned long long, uint32_t>::type;
     extern __shared__ __align__(128) unsigned char smem[];
+    // DUAL: one CTA per SM carries TWO independent groups of 32 syndromes ("teams" of W warps, each with its own
+    // messages, state, queue and block barrier) that take turns in the FP64-bound check pass: a team enters its check
+    // pass only when the other one has left its own, so that one team's check pass runs against the other's
+    // variable pass / bookkeeping (which leave the FP64 pipe idle) instead of against its check pass.  Two independent
+    // CTAs per SM drift into exactly that contention (measured: both in the check pass, then both out of it).
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int W = blockDim.x >> 5;
+    const int W = DUAL ? (blockDim.x >> 6) : (blockDim.x >> 5);   // warps per team
+    const int team = DUAL ? static_cast<int>(threadIdx.x >> 5) / W : 0;
+    const int warp = static_cast<int>(threadIdx.x >> 5) - team * W;   // warp index inside the team
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t ml = sbase + lane * 8;                         // this lane's message column
-    const uint32_t syn_own = sbase + p.off_syn + lane * 4;        // this lane's syndrome words, [word][32] layout
-    const uint32_t res0 = sbase + p.off_resid + lane * 4;         // residual buffers 0 / 1 of this lane
+    const uint32_t goff = DUAL ? static_cast<uint32_t>(team * p.group_stride) : 0u;   // this team's group of arrays
+    const uint32_t gbase = sbase + goff;
+    const uint32_t ml = gbase + lane * 8;                         // this lane's message column
+    const uint32_t syn_own = gbase + p.off_syn + lane * 4;        // this lane's syndrome words, [word][32] layout
+    const uint32_t res0 = gbase + p.off_resid + lane * 4;         // residual buffers 0 / 1 of this lane
     const uint32_t res_sum = 2 * res0 + p.SW * 128;               // res0 + res1
-    const uint32_t stage_a = sbase + p.off_stage;                 // [2][SW][32] staged syndromes of the queue window
+    const uint32_t stage_a = gbase + p.off_stage;                 // [2][SW][32] staged syndromes of the queue window
+    auto team_sync = [&]() {                                      // block barrier of this team
+        if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(W * 32) : "memory");
+        else __syncthreads();
+    };
+    // The check-pass token (DUAL).  Hardware barrier 3 + t is waited on by team t and arrived at by the other team;
+    // exactly one token exists (team 1 hands it to team 0 in the prologue) and a team only ever passes it on after
+    // having received it, so arrivals can never pile up on a barrier nobody waits on.  A team that has drained its
+    // queue takes one last (empty) turn, raises team_done and passes the token for good; the other team learns of it
+    // through `other_done`, which one thread samples and the team reads after its next block barrier, so that all
+    // warps of a team always agree on whether they take part in the hand-over.
+    volatile int *team_done = reinterpret_cast<volatile int *>(smem + p.off_mbar + 8);   // [2] raised by a finished team
+    volatile int *team_seen = team_done + 2;                                             // [2] team t's sample of team_done[t^1]
+    bool other_done = false;
+    auto token_wait = [&]() {
+        if constexpr (DUAL) {
+            if (!other_done) asm volatile("bar.sync %0, %1;" ::"r"(3 + team), "r"(2 * W * 32) : "memory");
+        }
+    };
+    auto token_pass = [&]() {
+        if constexpr (DUAL) {
+            if (!other_done) asm volatile("bar.arrive %0, %1;" ::"r"(3 + (team ^ 1)), "r"(2 * W * 32) : "memory");
+        }
+    };
     const uint32_t colptr_a = sbase + p.off_tables + p.off_colptr;
     const uint32_t ve_a = sbase + p.off_tables + p.off_ve;        // u32 byte offset of each edge's slot row
     const uint32_t vflip_a = sbase + p.off_tables + p.off_vflip;  // u16 residual word offset | bit of each edge's check
@@ -103,7 +134,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     if (threadIdx.x == 0) tma_load_tables(smem + p.off_tables, p.tables, static_cast<uint32_t>(p.tables_bytes), mbar);
 
     // This CTA's queue: 32-syndrome chunks c, c+G, c+2G, ... of the batch (B < 2^31 - 32*G, host-checked).
-    const int G = gridDim.x, c = blockIdx.x;
+    const int G = DUAL ? 2 * gridDim.x : gridDim.x, c = DUAL ? 2 * blockIdx.x + team : blockIdx.x;
     const int Bn = static_cast<int>(p.B);
     const int nchunks = (Bn + 31) >> 5;
     const int Q = (c < nchunks) ? (((nchunks - c + G - 1) / G) << 5) : 0;
@@ -118,7 +149,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         const int sid = sid_of(q_head + lane);
         if (sid >= 0) {
             const uint32_t *src = p.syn_words + static_cast<size_t>(sid) * p.SW;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + p.off_stage) + buf * p.SW * 32 + lane;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + goff + p.off_stage) + buf * p.SW * 32 + lane;
             for (int w = 0; w < p.SW; ++w) cp_async4(dst + w * 32, src + w);
         }
     };
@@ -131,9 +162,11 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     ebits_t ebits = 0;                                    // decisions of the variables this warp owns (bit i <-> j = warp + i*W)
     unsigned long long n_done = 0, n_conv = 0, n_iters = 0;   // warp wO only
 
+    if (DUAL && threadIdx.x < 4) team_done[threadIdx.x] = 0;   // team_done[2], team_seen[2]
     if (warp == wP) { prefetch(0, 0); cp_async_wait_all(); }
     __syncthreads();
     mbar_wait(mbar, 0);                                   // tables have landed
+    if (DUAL && team == 1) token_pass();                  // team 0 takes the first turn
 
     // Lanes in `mask` take the next queue entries (identically in every warp: the lane state is replicated).
     auto refill = [&](uint32_t mask) {
@@ -175,6 +208,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     if constexpr (prof) pt = static_cast<uint32_t>(clock64());
     while (any_active != 0u) {
         // ------------------------------------------------------------------ check pass (:135-150)
+        token_wait();
         if (active) {
             int i = warp;
             for (int g = 0; g < p.seg.ncseg; ++g) {
@@ -199,9 +233,11 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         }
         fresh = false;
         syn_a = syn_own;                                   // (wS copied the staged syndrome into the lane's own rows at refill time)
+        token_pass();
         tick(0);
-        __syncthreads();
+        team_sync();
         tick(1);
+        if (DUAL && warp == 0 && lane == 0) team_seen[team] = team_done[team ^ 1];   // read by the whole team after the next barrier
         // --------------------------------------------------------------- variable pass (:152-178)
         if (active) {
             ebits_t newbits = 0;
@@ -317,8 +353,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         }
         tick(3);
         if (warp == wP) cp_async_wait_all();                  // staged window complete before anyone reads it
-        __syncthreads();
+        team_sync();
         tick(4);
+        if constexpr (DUAL) other_done = team_seen[team] != 0;
         // ---------------------------------------- syndrome re-check, early stop, refill (:180-184)
         uint32_t r = 0;
         for (int w = 0; w < p.SW; ++w) r |= lds_u32(res_a + w * 128);
@@ -364,6 +401,11 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         }
         tick(6);
         if constexpr (prof) pc[7] += 1;
+    }
+    if constexpr (DUAL) {                                  // this team is finished: one last, empty turn
+        token_wait();
+        if (warp == 0 && lane == 0) { team_done[team] = 1; __threadfence_block(); }   // raised before this thread's arrival below
+        token_pass();
     }
     if (prof && p.prof != nullptr && lane == 0)
         for (int k = 0; k < 8; ++k) atomicAdd(p.prof + k, static_cast<unsigned long long>(pc[k]));

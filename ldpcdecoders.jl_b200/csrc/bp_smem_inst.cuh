@@ -49,4 +49,29 @@ void BPS_NAME(smem_kernel_launch_)(int shape, int eb64, int grid, int threads, i
     if (shape == kShape512x1) { if (eb64) smem_launch_one<512, 1, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<512, 1, false>(grid, threads, smem_bytes, st, p); }
 }
 
+
+// ---- dual-team form: one CTA of 2 x W warps per SM (bp_smem_kernel<512, 1, EB64, PROF, true>)
+cudaError_t BPS_NAME(smem_dual_attrs_)(int eb64, int smem_bytes, int threads, int *bps)
+{
+    auto set = [&](auto k) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, k, threads, smem_bytes);
+    };
+    return eb64 ? set(bp_smem_kernel<512, 1, true, false, true>) : set(bp_smem_kernel<512, 1, false, false, true>);
+}
+
+void BPS_NAME(smem_dual_launch_)(int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p)
+{
+    auto go = [&](auto k) {
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return;
+        k<<<grid, threads, smem_bytes, st>>>(p);
+    };
+    if (!eb64 && p.prof != nullptr) go(bp_smem_kernel<512, 1, false, true, true>);      // phase-timing build (diagnostics)
+    else if (eb64) go(bp_smem_kernel<512, 1, true, false, true>);
+    else go(bp_smem_kernel<512, 1, false, false, true>);
+}
+
 }  // namespace bp

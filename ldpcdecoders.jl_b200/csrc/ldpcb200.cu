@@ -202,6 +202,8 @@ struct ldpcb200 {
     int nfw = 0;                 // decision-field words per thread (0: fields live in registers)
     bool efield_global = false;
     bool lean = false, eb64 = false;   // bp_smem_kernel selected / its decision fields are 64 bits wide
+    bool dual = false;                 // ... in its two-teams-per-CTA form
+    int opt_dual = 0;                  // (measured equal to two independent CTAs per SM on C3: kept as an option)
     bp::KernelParams kp_proto{};
     std::vector<DeviceCtx> dev;
     std::atomic<long long> launches{0};
@@ -252,18 +254,25 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
 
 // shared-memory carve-up of bp_smem_kernel (bp_smem.cuh):
 //   messages | syn [SW][32] | resid [2][SW][32] | stage [2][SW][32] | tables | mbar
-int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p)
+//   dual: the first four arrays twice (one group per team, group_stride apart), then tables | mbar | team flags
+int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p, bool dual = false)
 {
     long long off = static_cast<long long>(h->E) * 32 * 8;
     p.off_syn = static_cast<int>(off);    off += h->SW * 128;
     p.off_resid = static_cast<int>(off);  off += 2 * h->SW * 128;      // per-lane double buffer
     p.off_stage = static_cast<int>(off);  off += 2 * h->SW * 128;      // double-buffered queue window
     p.off_nnz = p.off_efield = 0;
+    p.group_stride = 0;
+    if (dual) {
+        off = (off + 127) / 128 * 128;
+        p.group_stride = static_cast<int>(off);
+        off *= 2;
+    }
     off = (off + 15) / 16 * 16;
     p.off_tables = static_cast<int>(off);
     off += static_cast<long long>(h->tables.size());
     off = (off + 7) / 8 * 8;
-    p.off_mbar = static_cast<int>(off);   off += 8;
+    p.off_mbar = static_cast<int>(off);   off += 8 + 16;                // mbarrier + team_done[2] + team_seen[2]
     off = (off + 127) / 128 * 128;
     p.pd = 0; p.ring_slot_bytes = 0; p.ring_warp_bytes = 0; p.off_ring = static_cast<int>(off);
     return off > 0x7fffffff ? 0x7fffffff : static_cast<int>(off);
@@ -670,7 +679,7 @@ int configure(ldpcb200 *h)
     }
     shape = kernel_shape(two, warps * 32);
     // round-2 kernel for the shared-memory family: regular-enough codes whose decisions fit in a register per warp
-    bool lean = false, eb64 = false;
+    bool lean = false, eb64 = false, dual = false;
     int want_cv = 0;                 // contiguous variable ownership (uniform variable degree, caller's variable order)
     if (mode == 0 && h->opt_lean && !h->big && nfw == 0 && h->segs.ncseg > 0 && h->segs.nvseg > 0) {
         const int budget = two ? per_cta_2 : d0.smem_optin;
@@ -682,6 +691,10 @@ int configure(ldpcb200 *h)
             if (need_l <= budget) {
                 lean = true; need = need_l; kp = kl;
                 eb64 = (h->n + warps - 1) / warps > 32;
+                // two groups in one CTA per SM taking turns in the check pass (see bp_smem.cuh) instead of two independent CTAs
+                bp::KernelParams kd{};
+                const int need_d = smem_layout_lean(h, kd, true);
+                if (two && h->opt_dual && warps <= 8 && need_d <= d0.smem_optin) { dual = true; need = need_d; kp = kd; }
             } else if (want_cv) {
                 want_cv = 0;          // the padded table does not fit: interleaved ownership
             } else {
@@ -708,8 +721,11 @@ int configure(ldpcb200 *h)
     for (DeviceCtx &d : h->dev) {
         CU(cudaSetDevice(d.device));
         if (lean) {
-            cudaError_t e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_kernel_attrs_1(shape, eb64, need, warps * 32, &bps)
-                                                                  : bp::smem_kernel_attrs_0(shape, eb64, need, warps * 32, &bps);
+            cudaError_t e;
+            if (dual) e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_dual_attrs_1(eb64, need, 2 * warps * 32, &bps)
+                                                                : bp::smem_dual_attrs_0(eb64, need, 2 * warps * 32, &bps);
+            else e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_kernel_attrs_1(shape, eb64, need, warps * 32, &bps)
+                                                             : bp::smem_kernel_attrs_0(shape, eb64, need, warps * 32, &bps);
             if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "kernel attributes (shared-memory kernel): %s", cudaGetErrorString(e));
         } else {
             rc = kernel_attrs_dispatch(h->variant, mode, h->big, shape, need, warps * 32, &bps);
@@ -720,8 +736,8 @@ int configure(ldpcb200 *h)
     if (h->opt_max_ctas > 0) bps = std::min(bps, h->opt_max_ctas);
     h->family = family; h->mode = mode; h->warps = warps; h->shape = shape; h->ctas_per_sm = bps;
     h->smem_bytes = need; h->nfw = nfw; h->efield_global = ef_global; h->kp_proto = kp;
-    h->lean = lean; h->eb64 = eb64;
-    h->slots = 32 * bps * d0.sm_count;
+    h->lean = lean; h->eb64 = eb64; h->dual = dual;
+    h->slots = (dual ? 64 : 32) * bps * d0.sm_count;
     h->configured = true;
     return 0;
 }
@@ -821,9 +837,16 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             q.B = Bl;
             q.syn_words = syn_words + b0 * h->SW; q.err_words = err_words + b0 * h->NW; q.conv = conv + b0;
             q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
-            const int gl = static_cast<int>(std::min<long long>((Bl + 31) / 32, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
-            if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_kernel_launch_1(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
-            else bp::smem_kernel_launch_0(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+            const long long groups = (Bl + 31) / 32;
+            if (h->dual) {
+                const int gl = static_cast<int>(std::min<long long>((groups + 1) / 2, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
+                if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_dual_launch_1(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
+                else bp::smem_dual_launch_0(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
+            } else {
+                const int gl = static_cast<int>(std::min<long long>(groups, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
+                if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_kernel_launch_1(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+                else bp::smem_kernel_launch_0(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+            }
             h->launches++;
         }
     } else {
@@ -1380,6 +1403,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "lean") h->opt_lean = value ? 1 : 0;
+    else if (k == "dual") h->opt_dual = value ? 1 : 0;
     else if (k == "contiguous_variables") h->opt_cv = value ? 1 : 0;
     else if (k == "kernel_profile") { h->opt_kernel_profile = value ? 1 : 0; return 0; }
     else if (k == "max_ctas_per_sm") h->opt_max_ctas = static_cast<int>(value);
@@ -1400,7 +1424,7 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
     out->max_check_degree = h->max_cdeg; out->max_var_degree = h->max_vdeg;
     out->family = h->family; out->ndev = static_cast<int>(h->dev.size());
     out->sm_count = h->dev[0].sm_count;
-    out->ctas_per_sm = h->ctas_per_sm; out->threads_per_cta = h->warps * 32;
+    out->ctas_per_sm = h->ctas_per_sm; out->threads_per_cta = h->warps * 32 * (h->dual ? 2 : 1);
     out->smem_bytes = h->smem_bytes; out->slots = h->slots;
     out->syn_words = h->SW; out->err_words = h->NW;
     out->message_bytes = h->family == LDPCB200_FAMILY_SMEM
@@ -1408,7 +1432,7 @@ int ldpcb200_info(const ldpcb200_t *hc, ldpcb200_info_t *out)
                              : static_cast<int64_t>(h->slots) * std::max<int64_t>(h->E, 1) * 8;
     out->kernel_mode = h->mode;
     out->prefetch_distance = h->kp_proto.pd;
-    out->kernel_rev = h->lean ? 2 : 1;
+    out->kernel_rev = h->lean ? (h->dual ? 3 : 2) : 1;
     nccl_prepare(h);
     out->counters_via_nccl = h->nccl_state == 1 ? 1 : 0;
     return 0;

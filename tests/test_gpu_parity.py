@@ -63,9 +63,13 @@ def test_parity_configs(pkg, oracle, codes, name, per, B, families):
         assert g["info"]["family"] == fam
         assert_same(g, ref, want_ratio=True)
         if fam == SMEM:
-            # the shared-memory family has two kernels: the round-2 one (default where the code fits its envelope)
-            # and the general persistent kernel (lean = 0); both must replay the reference bit for bit
+            # the shared-memory family has three forms: the round-2 kernel (default where the code fits its envelope),
+            # the same kernel with two teams per CTA taking turns in the check pass (dual = 1) and the general
+            # persistent kernel (lean = 0); all must replay the reference bit for bit
             assert g["info"]["kernel_rev"] == 2, g["info"]
+            g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True, dual=1)
+            assert g["info"]["kernel_rev"] == 3
+            assert_same(g, ref, want_ratio=True)
             g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True, lean=0)
             assert g["info"]["kernel_rev"] == 1
             assert_same(g, ref, want_ratio=True)
@@ -94,7 +98,7 @@ def test_auto_family_selection(pkg, codes):
         dec.close()
         assert info["family"] == fam, (name, info)
         if fam == SMEM:
-            assert info["ctas_per_sm"] == 2, info
+            assert info["ctas_per_sm"] == 2 and info["slots"] == 64 * info["sm_count"], info
 
 
 @pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 95, 1000])
@@ -106,6 +110,7 @@ def test_ragged_batches(pkg, oracle, codes, B, fam):
     # small_batch = 0: keep these small batches on the persistent (lane-per-syndrome) kernel
     assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0), ref)
     if fam == SMEM:
+        assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0, dual=1), ref)
         assert_same(run_gpu(pkg, H, 0.06, mi, syn, family=fam, small_batch=0, lean=0), ref)
 
 
