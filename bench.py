@@ -36,7 +36,7 @@ UNIT = "syndromes/s"
 #   exact : the reference arithmetic is 10 add/sub/mul + 2 IEEE divisions of D = 8 FP64-pipe instructions each = 26
 #           (the algorithmic model of SURVEY 8(d)); the kernels EXECUTE 21 (products with +-1 and unread values dropped).
 #   minsum: 2 compares + 1 multiply per edge on the check side, 2 additions on the variable side = 5; no divisions.
-FP64_SLOTS = {"exact": {"model": 26, "executed": 21}, "minsum": {"model": 5, "executed": 5}}
+FP64_SLOTS = {"exact": {"model": 26, "executed": 21}, "minsum": {"model": 5, "executed": 5}, "fast": {"model": 4, "executed": 4}}
 FP64_LANES_PER_SM_CLK = 64
 WORKLOAD_NAMES = {"C1": "Gallager (1000,10,9)", "C2": "d=15 rotated surface X checks", "C3": "[[144,12,12]] gross code H_X",
                   "C4": "HGP of Gallager(32,4,3) H_X", "C5": "Gallager (100002,6,3)"}
@@ -418,7 +418,7 @@ def main():
                     help="phase timing of the shared-memory kernel (adds clock reads; not a bench value)")
     ap.add_argument("--max-ctas", type=int, default=0, dest="max_ctas", help="cap on resident CTAs per SM (experiments)")
     ap.add_argument("--lean", type=int, default=-1, help="family SMEM: 1 = round-2 kernel (default), 0 = general persistent kernel")
-    ap.add_argument("--variant", default="exact", choices=["exact", "minsum"],
+    ap.add_argument("--variant", default="exact", choices=["exact", "minsum", "fast"],
                     help="exact = reference-parity sum-product (headline); minsum = normalised min-sum (no reference equivalent)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -622,7 +622,23 @@ def main():
                           "note": "FP64 log-likelihood-ratio min-sum, same schedule/early stop; sum-product exact_match_frac is the line's own; "
                                   "5 FP64-pipe slots per edge-iteration (no divisions): the kernel is issue/shared-memory bound, not FP64 bound"}
         dms.close()
-        del errw_sp, rms
+        del rms
+        # the fast FP32 tanh/atanh variant (north star): quality against the exact kernels on the same syndromes
+        dfa = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant="fast")
+        rfa = DeviceRun(torch, dev, stream, dfa, B)
+        rfa.sample(per)
+        secs3, c3_, _ = rfa.timed(3, 2, flush)
+        differ = int((rfa.errw != errw_sp).any(dim=1).sum().item()) if run.tile >= B else None
+        line["fast32"] = {"value": float(c3_[0]) / secs3, "unit": UNIT, "per": per,
+                          "mean_iters": float(c3_[2]) / float(c3_[0]), "converged_frac": float(c3_[1]) / float(c3_[0]),
+                          "exact_match_frac": rfa.exact_match_frac_last_tile(per),
+                          "decisions_differ_from_exact_frac": differ / B if differ is not None else None,
+                          "kernel": {k: rfa.info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "kernel_rev")},
+                          "note": "FP32 log-likelihood-ratio tanh/atanh sum-product with MUFU EX2/RCP/LG2, same schedule/early stop; messages "
+                                  "travel through the same 8-byte shared-memory slots (kernel structure shared with the exact variant); "
+                                  "not bit-compatible with the reference: compare exact_match_frac / converged_frac with the line's own"}
+        dfa.close()
+        del errw_sp, rfa
 
     # ---- BASELINE.json config 4 is "the BP stage of BP+OSD": the whole BP -> OSD-0 pipeline on the same syndromes
     # (ldpcb200_decode_device with posterior ratios, then ldpcb200_osd0_device on the unconverged ones)

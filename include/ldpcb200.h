@@ -50,6 +50,10 @@ typedef struct ldpcb200 ldpcb200_t;
 #define LDPCB200_VARIANT_MINSUM 1 /* min-sum on FP64 log-likelihood ratios; NO reference equivalent (the package's BP is
                                      sum-product): a faster, non-bit-compatible option.  Same schedule, early stop and
                                      outputs; posterior_ratio then carries the posterior LLR log(P0/P1). */
+#define LDPCB200_VARIANT_FAST32 2 /* FP32 tanh/atanh sum-product on log-likelihood ratios with the special-function unit (MUFU
+                                     EX2 / RCP / LG2); the clamped textbook form of bpots_decoder.jl:182-211 on the BP decoder's
+                                     schedule.  Fast, NOT bit-compatible with the reference: judged by mismatch rate and logical
+                                     error rate against the exact variant (bench.py reports both).  posterior_ratio = posterior LLR. */
 
 /* kernel families (ldpcb200_info_t.family, option "family") */
 #define LDPCB200_FAMILY_AUTO   0
@@ -176,6 +180,32 @@ int ldpcb200_sample_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, int64_t f
 int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
                           const uint32_t *d_true_err_words, const uint32_t *d_err_words,
                           const uint32_t *d_syn_words, unsigned long long *d_out, void *stream);
+
+/* Logical operators for failure counting: L is k x n over GF(2), k <= 64, given like H by its CSC arrays.  A decoded error
+ * e' fails on the true error e when H*e' != syndrome or L*(e xor e') != 0.  k = 0 removes them (failure = e' != e, the
+ * criterion of test/test_bp_decoder.jl:27-28). */
+int ldpcb200_set_logicals(ldpcb200_t *h, int64_t k, const int64_t *colptr, const int64_t *rowval, int32_t index_base);
+
+/* ldpcb200_score_device with failure counting: ADDS into d_out[4] (uint64): [0] exact matches, [1] rows whose decoded error
+ * reproduces the syndrome, [2] failures (see ldpcb200_set_logicals), [3] total weight of e xor e'. */
+int ldpcb200_score_logical_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_true_err_words,
+                                  const uint32_t *d_err_words, const uint32_t *d_syn_words, unsigned long long *d_out,
+                                  void *stream);
+
+/* Prior of an existing handle (channel_probs of belief_propagation.jl:8,89): lets an error-rate sweep reuse the
+ * device-resident Tanner graph.  Same rules as the `per` of ldpcb200_create. */
+int ldpcb200_set_per(ldpcb200_t *h, double per);
+
+/* The sampling + scoring harness (pattern of test/test_bp_decoder.jl:19-30 with the batch generated where it
+ * is decoded): `shots` i.i.d. Bernoulli(per_channel) errors from the Philox stream (seed, global indices first ..
+ * first+shots-1), their syndromes, BP with the handle's prior and max_iters (followed by OSD-0 on the unconverged ones when
+ * osd != 0), scoring against the true errors -- sharded over the handle's devices in device-resident tiles; nothing but the
+ * counters crosses PCIe.  The per-device counters are summed with one ncclAllReduce when the handle has communicators, else
+ * on the host.  out[8]: [0] shots decoded, [1] converged, [2] BP iterations, [3] exact matches, [4] syndrome satisfied,
+ * [5] failures (logical failures when logical operators are set), [6] weight of e xor e', [7] syndromes sent to OSD-0. */
+#define LDPCB200_NUM_HARNESS_COUNTERS 8
+int ldpcb200_sample_decode_score(ldpcb200_t *h, int64_t shots, int64_t first, uint64_t seed, double per_channel,
+                                 int32_t osd, int64_t *out);
 
 /* Self-test of the kernels' branch-free division sequences against the stock IEEE routines
  * (__drcp_rn / __ddiv_rn) on n pseudo-random operands of envelope `mode` (0: t = 2/(1+q)-1,

@@ -7,7 +7,7 @@ reference's decoder interface on top of that ABI; codes.py builds the benchmark 
 from . import _lib, codes, sharding                                              # noqa: F401
 from .decoder import (BeliefPropagationDecoder, BeliefPropagationOSDDecoder,     # noqa: F401
                       BeliefPropagationScratchSpace,
-                      decode_b, batchdecode_b, reset_b)
+                      decode_b, batchdecode_b, reset_b, ler_curve)
 
 __all__ = ["BeliefPropagationDecoder", "BeliefPropagationOSDDecoder", "BeliefPropagationScratchSpace", "decode_b", "batchdecode_b",
-           "reset_b", "codes"]
+           "reset_b", "ler_curve", "codes"]

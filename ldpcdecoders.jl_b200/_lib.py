@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libldpcb200.so")
 OK, EINVAL, ECUDA, ENODEVICE, EUNSUPPORTED, ENOMEM = range(6)
 FMT_U8, FMT_I64, FMT_BITS, FMT_PACKED32, FMT_F64 = range(5)
 FAMILY_AUTO, FAMILY_SMEM, FAMILY_GLOBAL = range(3)
-VARIANT_EXACT, VARIANT_MINSUM = 0, 1
+VARIANT_EXACT, VARIANT_MINSUM, VARIANT_FAST32 = 0, 1, 2
 NUM_COUNTERS = 4
 NUM_OSD_STATS = 3      # processed, pivots, columns visited
 CTR_DECODED, CTR_CONVERGED, CTR_ITERATIONS = 0, 1, 2
@@ -24,7 +24,10 @@ SYMBOLS = [
     "ldpcb200_decode_device", "ldpcb200_sample_device", "ldpcb200_score_device",
     "ldpcb200_launch_count", "ldpcb200_selftest_division",
     "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device", "ldpcb200_kernel_profile",
+    "ldpcb200_set_logicals", "ldpcb200_score_logical_device", "ldpcb200_set_per", "ldpcb200_sample_decode_score",
 ]
+NUM_HARNESS_COUNTERS = 8
+HARNESS_FIELDS = ("shots", "converged", "iterations", "exact_matches", "syndrome_satisfied", "failures", "residual_weight", "osd_processed")
 
 
 class Info(ctypes.Structure):
@@ -72,6 +75,10 @@ def load():
     lib.ldpcb200_osd0_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.ldpcb200_sample_device.argtypes = [vp, i32, i64, i64, u64, dbl, vp, vp, vp]
     lib.ldpcb200_score_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.ldpcb200_set_logicals.argtypes = [vp, i64, vp, vp, i32]
+    lib.ldpcb200_score_logical_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.ldpcb200_set_per.argtypes = [vp, dbl]
+    lib.ldpcb200_sample_decode_score.argtypes = [vp, i64, i64, u64, dbl, i32, ctypes.POINTER(i64)]
     lib.ldpcb200_kernel_profile.argtypes = [vp, i32, ctypes.POINTER(i64), i32]
     lib.ldpcb200_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ldpcb200_selftest_division.argtypes = [i32, i32, u64, u64, ctypes.POINTER(u64)]   # mismatches[4]

@@ -59,6 +59,83 @@ def surface_x(d):
     return _csc(rows, cols, (r_idx, d * d))
 
 
+def surface_z(d):
+    """Z checks of the same rotated surface code (the other colour of plaquettes; left/right boundary weight 2)."""
+    rows, cols = [], []
+    r_idx = 0
+    for r in range(d + 1):
+        for c in range(d + 1):
+            if (r + c) % 2 != 1:
+                continue                   # X-type plaquette
+            qs = [(rr, cc) for rr in (r - 1, r) for cc in (c - 1, c) if 0 <= rr < d and 0 <= cc < d]
+            bulk = 1 <= r <= d - 1 and 1 <= c <= d - 1
+            left_right = (c == 0 or c == d) and 1 <= r <= d - 1
+            if not (bulk or left_right):
+                continue
+            for (rr, cc) in qs:
+                rows.append(r_idx)
+                cols.append(rr * d + cc)
+            r_idx += 1
+    return _csc(rows, cols, (r_idx, d * d))
+
+
+def _gf2_rref(M):
+    """Reduced row echelon form over GF(2) of a dense 0/1 array; returns (R, pivot columns)."""
+    R = (np.array(M, dtype=np.uint8) & 1).copy()
+    piv = []
+    r = 0
+    for c in range(R.shape[1]):
+        if r >= R.shape[0]:
+            break
+        hit = np.nonzero(R[r:, c])[0]
+        if hit.size == 0:
+            continue
+        k = r + hit[0]
+        if k != r:
+            R[[r, k]] = R[[k, r]]
+        rows = np.nonzero(R[:, c])[0]
+        rows = rows[rows != r]
+        R[rows] ^= R[r]
+        piv.append(c)
+        r += 1
+    return R[:r], piv
+
+
+def gf2_nullspace(M):
+    """Basis (rows) of {x : M x = 0 over GF(2)}."""
+    M = (np.array(M, dtype=np.uint8) & 1)
+    n = M.shape[1]
+    R, piv = _gf2_rref(M)
+    free = [c for c in range(n) if c not in set(piv)]
+    N = np.zeros((len(free), n), dtype=np.uint8)
+    for k, f in enumerate(free):
+        N[k, f] = 1
+        for r, pc in enumerate(piv):
+            if R[r, f]:
+                N[k, pc] = 1
+    return N
+
+
+def css_logicals(H_detect, H_other):
+    """Logical operators that tell harmless residuals from logical errors for a CSS code whose errors are detected by
+    H_detect: a basis of ker(H_other) modulo the row space of H_detect (k x n).  A residual r with H_detect r = 0 is a
+    stabilizer iff L r = 0.  (Gross code: 12 rows; rotated surface code: 1.)"""
+    Hd = np.asarray(sp.csc_matrix(H_detect).todense(), dtype=np.uint8) & 1
+    Ho = np.asarray(sp.csc_matrix(H_other).todense(), dtype=np.uint8) & 1
+    K = gf2_nullspace(Ho)                         # everything that commutes with the other check type
+    S, _ = _gf2_rref(Hd)
+    rank_s = S.shape[0]
+    L = []
+    cur = S.copy()
+    for v in K:                                   # keep kernel vectors that enlarge the span of the stabilizers
+        trial, _ = _gf2_rref(np.vstack([cur, v[None, :]]))
+        if trial.shape[0] > cur.shape[0]:
+            L.append(v)
+            cur = trial
+    assert cur.shape[0] == rank_s + len(L)
+    return sp.csc_matrix(np.array(L, dtype=np.uint8).reshape(len(L), Hd.shape[1]))
+
+
 def _shift(m):
     return sp.csc_matrix(np.roll(np.eye(m, dtype=np.int64), 1, axis=1))
 

@@ -18,6 +18,7 @@ enum KernelShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
     void kernel_launch_##M##_##B##_##V(int shape, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
 BP_DECLARE_MODE(0, 0, 0) BP_DECLARE_MODE(0, 1, 0) BP_DECLARE_MODE(1, 0, 0) BP_DECLARE_MODE(1, 1, 0) BP_DECLARE_MODE(2, 0, 0) BP_DECLARE_MODE(2, 1, 0)
 BP_DECLARE_MODE(0, 0, 1) BP_DECLARE_MODE(1, 0, 1) BP_DECLARE_MODE(2, 0, 1)
+BP_DECLARE_MODE(0, 0, 2) BP_DECLARE_MODE(1, 0, 2) BP_DECLARE_MODE(2, 0, 2)
 #undef BP_DECLARE_MODE
 
 // shared-memory-resident kernel of round 2 (bp_smem.cuh), one translation unit per variant V
@@ -26,7 +27,7 @@ BP_DECLARE_MODE(0, 0, 1) BP_DECLARE_MODE(1, 0, 1) BP_DECLARE_MODE(2, 0, 1)
     void smem_kernel_launch_##V(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p); \
     cudaError_t smem_dual_attrs_##V(int eb64, int smem_bytes, int threads, int *blocks_per_sm);                  \
     void smem_dual_launch_##V(int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
-BP_DECLARE_SMEM(0) BP_DECLARE_SMEM(1)
+BP_DECLARE_SMEM(0) BP_DECLARE_SMEM(1) BP_DECLARE_SMEM(2)
 #undef BP_DECLARE_SMEM
 
 }  // namespace bp

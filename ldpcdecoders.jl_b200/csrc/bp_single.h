@@ -23,5 +23,6 @@ struct SingleParams {
 constexpr int kSingleThreads = 512;
 cudaError_t single_launch_0(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);   // exact variant
 cudaError_t single_launch_1(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);   // min-sum variant
+cudaError_t single_launch_2(int grid, int smem_bytes, cudaStream_t st, const SingleParams &p);   // fast FP32 variant
 
 }  // namespace bp

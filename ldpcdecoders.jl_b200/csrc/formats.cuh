@@ -194,4 +194,66 @@ __global__ void score_rows(const int *__restrict__ rowptr_unused, const int *__r
     }
 }
 
+// Scoring with logical operators (pattern of test/test_bp_decoder.jl:19-30 with the comparison a QEC
+// caller really wants): r = truth xor decoded is a failure when it is detectable (H*decoded != syndrome) or acts on the
+// logical qubits (L*r != 0, lmask[j] = column j of the k x n matrix L, k <= 64, as a bit mask).  Without logical
+// operators (lmask == nullptr) a failure is `decoded != truth`, the reference test's own criterion.
+// out[0] += exact matches, out[1] += rows with H*decoded == syndrome, out[2] += failures, out[3] += residual weight.
+// One warp per row.
+__global__ void score_rows_logical(const int *__restrict__ colptr, const int *__restrict__ ve_chk, int NW, int SW, long long B,
+                                   const uint32_t *__restrict__ truth, const uint32_t *__restrict__ dec,
+                                   const uint32_t *__restrict__ syn, uint32_t *__restrict__ scratch_syn,
+                                   const unsigned long long *__restrict__ lmask, unsigned long long *out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    unsigned long long exact = 0, consistent = 0, failures = 0, weight = 0;
+    for (long long b = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        uint32_t *row = scratch_syn + b * SW;
+        for (int w = lane; w < SW; w += 32) row[w] = 0u;
+        __syncwarp();
+        bool same = true;
+        unsigned long long lacc = 0;
+        int wt = 0;
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t v = dec[b * NW + w];
+            uint32_t r = v ^ truth[b * NW + w];
+            same &= r == 0u;
+            wt += __popc(r);
+            while (v) {                                   // syndrome of the decoded error
+                const int j = w * 32 + (__ffs(v) - 1);
+                v &= v - 1;
+                for (int e = colptr[j]; e < colptr[j + 1]; ++e) {
+                    const int chk = ve_chk[e];
+                    atomicXor(row + (chk >> 5), 1u << (chk & 31));
+                }
+            }
+            if (lmask)
+                while (r) {                               // action of the residual on the logical qubits
+                    lacc ^= lmask[w * 32 + (__ffs(r) - 1)];
+                    r &= r - 1;
+                }
+        }
+        same = __all_sync(0xffffffffu, same);
+        for (int o = 16; o > 0; o >>= 1) {
+            lacc ^= __shfl_xor_sync(0xffffffffu, lacc, o);
+            wt += __shfl_xor_sync(0xffffffffu, wt, o);
+        }
+        __syncwarp();
+        bool ok = true;
+        for (int w = lane; w < SW; w += 32) ok &= row[w] == syn[b * SW + w];
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) {
+            exact += same; consistent += ok; weight += wt;
+            failures += lmask ? (!ok || lacc != 0ull) : !same;
+        }
+    }
+    if (lane == 0) {
+        if (exact) atomicAdd(out + 0, exact);
+        if (consistent) atomicAdd(out + 1, consistent);
+        if (failures) atomicAdd(out + 2, failures);
+        if (weight) atomicAdd(out + 3, weight);
+    }
+}
+
 }  // namespace bp

@@ -158,6 +158,8 @@ struct DeviceCtx {
     } set[2];
     cudaEvent_t decode_done = nullptr;
     DevBuf counters, scratch, osd_stats, kprof, ctr_sum;
+    DevBuf lmask;                                         // logical operators: one 64-bit mask per variable (or empty)
+    DevBuf hs_truth, hs_syn, hs_err, hs_conv, hs_iters, hs_ratio, hs_ctr, hs_sum;   // sampling + scoring harness tiles
     DevBuf tiny;            // small-batch host calls: one device block ...
     PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
@@ -213,6 +215,8 @@ struct ldpcb200 {
     int nccl_state = 0;                 // 0 not tried, 1 communicators ready, -1 unavailable (see nccl_why)
     std::string nccl_why;
     std::vector<ncclComm_t> comms;
+    std::vector<unsigned long long> lmask;   // logical operators as per-variable bit masks (empty: none)
+    int n_logicals = 0;
 };
 
 namespace {
@@ -515,7 +519,8 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum}) b->release();
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum, &d.lmask, &d.hs_truth, &d.hs_syn, &d.hs_err,
+                       &d.hs_conv, &d.hs_iters, &d.hs_ratio, &d.hs_ctr, &d.hs_sum}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
         for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
@@ -546,6 +551,12 @@ int kernel_attrs_dispatch(int variant, int mode, bool big, int shape, int smem_b
             case 1: e = bp::kernel_attrs_1_0_1(shape, smem_bytes, threads, bps); break;
             default: e = bp::kernel_attrs_2_0_1(shape, smem_bytes, threads, bps); break;
         }
+    } else if (variant == LDPCB200_VARIANT_FAST32) {
+        switch (mode) {
+            case 0: e = bp::kernel_attrs_0_0_2(shape, smem_bytes, threads, bps); break;
+            case 1: e = bp::kernel_attrs_1_0_2(shape, smem_bytes, threads, bps); break;
+            default: e = bp::kernel_attrs_2_0_2(shape, smem_bytes, threads, bps); break;
+        }
     } else {
         switch (mode * 2 + (big ? 1 : 0)) {
             case 0: e = bp::kernel_attrs_0_0_0(shape, smem_bytes, threads, bps); break;
@@ -568,6 +579,14 @@ void kernel_launch_dispatch(int variant, int mode, bool big, int shape, int grid
             case 0: bp::kernel_launch_0_0_1(shape, grid, threads, smem_bytes, st, p); break;
             case 1: bp::kernel_launch_1_0_1(shape, grid, threads, smem_bytes, st, p); break;
             default: bp::kernel_launch_2_0_1(shape, grid, threads, smem_bytes, st, p); break;
+        }
+        return;
+    }
+    if (variant == LDPCB200_VARIANT_FAST32) {
+        switch (mode) {
+            case 0: bp::kernel_launch_0_0_2(shape, grid, threads, smem_bytes, st, p); break;
+            case 1: bp::kernel_launch_1_0_2(shape, grid, threads, smem_bytes, st, p); break;
+            default: bp::kernel_launch_2_0_2(shape, grid, threads, smem_bytes, st, p); break;
         }
         return;
     }
@@ -722,10 +741,11 @@ int configure(ldpcb200 *h)
         CU(cudaSetDevice(d.device));
         if (lean) {
             cudaError_t e;
-            if (dual) e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_dual_attrs_1(eb64, need, 2 * warps * 32, &bps)
-                                                                : bp::smem_dual_attrs_0(eb64, need, 2 * warps * 32, &bps);
-            else e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::smem_kernel_attrs_1(shape, eb64, need, warps * 32, &bps)
-                                                             : bp::smem_kernel_attrs_0(shape, eb64, need, warps * 32, &bps);
+            const int v = h->variant;
+            if (dual) e = v == 1 ? bp::smem_dual_attrs_1(eb64, need, 2 * warps * 32, &bps)
+                        : v == 2 ? bp::smem_dual_attrs_2(eb64, need, 2 * warps * 32, &bps) : bp::smem_dual_attrs_0(eb64, need, 2 * warps * 32, &bps);
+            else e = v == 1 ? bp::smem_kernel_attrs_1(shape, eb64, need, warps * 32, &bps)
+                   : v == 2 ? bp::smem_kernel_attrs_2(shape, eb64, need, warps * 32, &bps) : bp::smem_kernel_attrs_0(shape, eb64, need, warps * 32, &bps);
             if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "kernel attributes (shared-memory kernel): %s", cudaGetErrorString(e));
         } else {
             rc = kernel_attrs_dispatch(h->variant, mode, h->big, shape, need, warps * 32, &bps);
@@ -781,7 +801,8 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             q.counters = counters;
             q.off_syn = off_syn; q.off_resid = off_syn + h->SW * 4; q.off_dec = off_syn + 2 * h->SW * 4;
             CU(h->variant == LDPCB200_VARIANT_MINSUM ? bp::single_launch_1(static_cast<int>(B), smem, st, q)
-                                                     : bp::single_launch_0(static_cast<int>(B), smem, st, q));
+               : h->variant == LDPCB200_VARIANT_FAST32 ? bp::single_launch_2(static_cast<int>(B), smem, st, q)
+                                                       : bp::single_launch_0(static_cast<int>(B), smem, st, q));
             h->launches++;
             return 0;
         }
@@ -841,10 +862,12 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             if (h->dual) {
                 const int gl = static_cast<int>(std::min<long long>((groups + 1) / 2, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
                 if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_dual_launch_1(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
+                else if (h->variant == LDPCB200_VARIANT_FAST32) bp::smem_dual_launch_2(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
                 else bp::smem_dual_launch_0(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
             } else {
                 const int gl = static_cast<int>(std::min<long long>(groups, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
                 if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_kernel_launch_1(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
+                else if (h->variant == LDPCB200_VARIANT_FAST32) bp::smem_kernel_launch_2(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
                 else bp::smem_kernel_launch_0(h->shape, h->eb64, gl, thr, h->smem_bytes, st, q);
             }
             h->launches++;
@@ -1271,33 +1294,103 @@ void nccl_prepare(ldpcb200 *h)
     h->nccl_state = 1;
 }
 
-// Sum the per-device counter blocks (d.counters, 4 x uint64, complete on d.set[0].stream) over all devices of the
+// Sum per-device counter blocks (`count` x uint64 at src(d), complete on d.set[0].stream) over all devices of the
 // handle with one grouped ncclAllReduce; the result of device 0 goes to `out`.
-int nccl_sum_counters(ldpcb200 *h, int64_t *out)
+template <class Src>
+int nccl_sum_block(ldpcb200 *h, int count, Src src, int64_t *out)
 {
     const int nd = static_cast<int>(h->dev.size());
     for (int k = 0; k < nd; ++k) {
         DeviceCtx &d = h->dev[k];
         CU(cudaSetDevice(d.device));
-        int rc = d.ctr_sum.reserve(LDPCB200_NUM_COUNTERS * 8);
+        int rc = d.ctr_sum.reserve(16 * 8);
         if (rc) return rc;
     }
     ncclResult_t r = g_nccl.GroupStart();
     for (int k = 0; k < nd && r == ncclSuccess; ++k) {
         DeviceCtx &d = h->dev[k];
-        r = g_nccl.AllReduce(d.counters.p, d.ctr_sum.p, LDPCB200_NUM_COUNTERS, ncclUint64, ncclSum, h->comms[k], d.set[0].stream);
+        r = g_nccl.AllReduce(src(d), d.ctr_sum.p, count, ncclUint64, ncclSum, h->comms[k], d.set[0].stream);
     }
     ncclResult_t r2 = g_nccl.GroupEnd();
     if (r == ncclSuccess) r = r2;
     if (r != ncclSuccess) return fail(LDPCB200_ECUDA, "ncclAllReduce of the counters: %s", g_nccl.GetErrorString(r));
-    unsigned long long hc[LDPCB200_NUM_COUNTERS];
+    unsigned long long hc[16];
     for (int k = 0; k < nd; ++k) {
         DeviceCtx &d = h->dev[k];
         CU(cudaSetDevice(d.device));
-        if (k == 0) CU(cudaMemcpyAsync(hc, d.ctr_sum.p, sizeof(hc), cudaMemcpyDeviceToHost, d.set[0].stream));
+        if (k == 0) CU(cudaMemcpyAsync(hc, d.ctr_sum.p, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, d.set[0].stream));
         CU(cudaStreamSynchronize(d.set[0].stream));
     }
-    for (int c = 0; c < LDPCB200_NUM_COUNTERS; ++c) out[c] = static_cast<int64_t>(hc[c]);
+    for (int c = 0; c < count; ++c) out[c] = static_cast<int64_t>(hc[c]);
+    return 0;
+}
+int nccl_sum_counters(ldpcb200 *h, int64_t *out)
+{
+    return nccl_sum_block(h, LDPCB200_NUM_COUNTERS, [](DeviceCtx &d) { return d.counters.p; }, out);
+}
+
+// One device's share of the sampling + scoring harness: tiles of device-resident shots.
+int harness_on_device(ldpcb200 *h, DeviceCtx &d, int64_t first, int64_t shots, uint64_t seed, double per_channel, bool osd,
+                      int64_t *out8)
+{
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = d.set[0].stream;
+    int rc;
+    if ((rc = d.hs_ctr.reserve(LDPCB200_NUM_HARNESS_COUNTERS * 8))) return rc;
+    CU(cudaMemsetAsync(d.hs_ctr.p, 0, LDPCB200_NUM_HARNESS_COUNTERS * 8, st));
+    if (shots > 0) {
+        // tile: bounded by 64 MB of packed rows (and 1 GB of posterior ratios when OSD follows)
+        int64_t tile = std::max<int64_t>(32, (64ll << 20) / (static_cast<int64_t>(h->SW + 2 * h->NW) * 4 + 5));
+        if (osd) tile = std::min<int64_t>(tile, std::max<int64_t>(32, (1ll << 30) / (h->n * 8)));
+        tile = std::min<int64_t>(std::max<int64_t>(tile, 2 * static_cast<int64_t>(h->slots)), shots);
+        if ((rc = d.hs_truth.reserve(static_cast<size_t>(tile) * h->NW * 4)) || (rc = d.hs_err.reserve(static_cast<size_t>(tile) * h->NW * 4)) ||
+            (rc = d.hs_syn.reserve(static_cast<size_t>(tile) * h->SW * 4)) || (rc = d.hs_conv.reserve(static_cast<size_t>(tile))) ||
+            (rc = d.hs_iters.reserve(static_cast<size_t>(tile) * 4)) || (rc = d.scratch.reserve(static_cast<size_t>(tile) * h->SW * 4)))
+            return rc;
+        if (osd && (rc = d.hs_ratio.reserve(static_cast<size_t>(tile) * h->n * 8))) return rc;
+        if (osd && (rc = d.osd_stats.reserve(64))) return rc;
+        if (osd) CU(cudaMemsetAsync(d.osd_stats.p, 0, 64, st));
+        if (!h->lmask.empty() && !d.lmask.p) {
+            if ((rc = d.lmask.reserve(h->lmask.size() * 8))) return rc;
+            CU(cudaMemcpyAsync(d.lmask.p, h->lmask.data(), h->lmask.size() * 8, cudaMemcpyHostToDevice, st));
+        }
+        double t = std::floor(per_channel * 4294967296.0);
+        const uint32_t thr = !(t > 0) ? 0u : (t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t));
+        unsigned long long *ctr = d.hs_ctr.as<unsigned long long>();
+        for (int64_t t0 = 0; t0 < shots; t0 += tile) {
+            const int64_t bt = std::min(tile, shots - t0);
+            CU(cudaMemsetAsync(d.hs_syn.p, 0, static_cast<size_t>(bt) * h->SW * 4, st));
+            bp::sample_errors<<<grid_for(bt * h->NW, d.sm_count), 256, 0, st>>>(static_cast<int>(h->n), h->NW, bt, first + t0,
+                                                                               static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), thr,
+                                                                               d.hs_truth.as<uint32_t>());
+            bp::syndrome_of<<<grid_for(bt * h->NW, d.sm_count), 256, 0, st>>>(d.d_colptr, d.d_ve_chk, h->NW, h->SW, bt, d.hs_truth.as<uint32_t>(),
+                                                                             d.hs_syn.as<uint32_t>());
+            h->launches += 2;
+            const bool want_ratio = osd && h->max_iters > 0;
+            rc = decode_on_device(h, d, bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(), d.hs_iters.as<int32_t>(),
+                                  want_ratio ? d.hs_ratio.as<double>() : nullptr, ctr, st, true);
+            if (rc) return rc;
+            if (osd) {
+                if (h->max_iters <= 0) {
+                    bp::osd_fill_ones_kernel<<<grid_for(bt * h->n, d.sm_count), 256, 0, st>>>(d.hs_ratio.as<double>(), bt * h->n);
+                    h->launches++;
+                }
+                rc = osd0_on_device(h, d, d.set[0], bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(),
+                                    d.hs_ratio.as<double>(), d.osd_stats.as<unsigned long long>(), st);
+                if (rc) return rc;
+            }
+            bp::score_rows_logical<<<grid_for(bt * 32, d.sm_count), 256, 0, st>>>(
+                d.d_colptr, d.d_ve_chk, h->NW, h->SW, bt, d.hs_truth.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_syn.as<uint32_t>(),
+                d.scratch.as<uint32_t>(), h->lmask.empty() ? nullptr : d.lmask.as<unsigned long long>(), ctr + 3);
+            h->launches++;
+            CU(cudaGetLastError());
+        }
+        if (osd) CU(cudaMemcpyAsync(ctr + 7, d.osd_stats.p, 8, cudaMemcpyDeviceToDevice, st));
+    }
+    unsigned long long hc[LDPCB200_NUM_HARNESS_COUNTERS];
+    CU(cudaMemcpyAsync(hc, d.hs_ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < LDPCB200_NUM_HARNESS_COUNTERS; ++k) out8[k] = static_cast<int64_t>(hc[k]);
     return 0;
 }
 
@@ -1332,10 +1425,10 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
         return fail(LDPCB200_EINVAL, "bad shape / null colptr / index_base not 0 or 1");
     if (s > 0x3fffffff || n > 0x3fffffff) return fail(LDPCB200_EINVAL, "matrix too large");
     if (!rowval && colptr[n] - index_base != 0) return fail(LDPCB200_EINVAL, "rowval is null");
-    if (variant != LDPCB200_VARIANT_EXACT && variant != LDPCB200_VARIANT_MINSUM)
+    if (variant != LDPCB200_VARIANT_EXACT && variant != LDPCB200_VARIANT_MINSUM && variant != LDPCB200_VARIANT_FAST32)
         return fail(LDPCB200_EUNSUPPORTED, "variant %d not available", variant);
-    if (variant == LDPCB200_VARIANT_MINSUM && !(per > 0.0 && per < 1.0))
-        return fail(LDPCB200_EINVAL, "the min-sum variant needs 0 < per < 1 (finite prior log-likelihood ratio)");
+    if (variant != LDPCB200_VARIANT_EXACT && !(per > 0.0 && per < 1.0))
+        return fail(LDPCB200_EINVAL, "the log-likelihood-ratio variants need 0 < per < 1 (finite prior)");
     if (max_iters < 0) max_iters = 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -1350,16 +1443,17 @@ int ldpcb200_create(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
         volatile double q = per / one_minus;
         h->p0 = q;
         h->regular_p0 = std::isnormal(h->p0) && h->p0 > 0.0;
-        if (variant == LDPCB200_VARIANT_MINSUM) {      // the kernels' prior slot carries L0 = log((1-p)/p)
+        if (variant != LDPCB200_VARIANT_EXACT) {        // the kernels' prior slot carries L0 = log((1-p)/p)
             volatile double r = one_minus / per;
             h->p0 = std::log(r);
+            if (variant == LDPCB200_VARIANT_FAST32) h->p0 = static_cast<double>(static_cast<float>(h->p0));
         }
     }
     int rc = build_graph(h, colptr, rowval, index_base);
     if (rc) { delete h; return rc; }
-    if (variant == LDPCB200_VARIANT_MINSUM && h->big) {
+    if (variant != LDPCB200_VARIANT_EXACT && h->big) {
         delete h;
-        return fail(LDPCB200_EUNSUPPORTED, "the min-sum variant supports node degrees up to %d", bp::kMaxRegDegree);
+        return fail(LDPCB200_EUNSUPPORTED, "the min-sum and fast variants support node degrees up to %d", bp::kMaxRegDegree);
     }
     std::vector<int> devs;
     if (devices && ndev > 0) devs.assign(devices, devices + ndev); else devs.push_back(0);
@@ -1586,6 +1680,120 @@ int ldpcb200_score_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint
                                                                 d.scratch.as<uint32_t>(), d_out);
     h->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int ldpcb200_set_logicals(ldpcb200_t *h, int64_t k, const int64_t *colptr, const int64_t *rowval, int32_t index_base)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (k < 0 || k > 64) return fail(LDPCB200_EUNSUPPORTED, "between 0 and 64 logical operators are supported (got %lld)", (long long)k);
+    if (k > 0 && (!colptr || (index_base != 0 && index_base != 1))) return fail(LDPCB200_EINVAL, "null colptr / bad index_base");
+    std::vector<unsigned long long> m;
+    if (k > 0) {
+        m.assign(std::max<int64_t>(h->n, 1), 0ull);
+        for (int64_t j = 0; j < h->n; ++j)
+            for (int64_t e = colptr[j] - index_base; e < colptr[j + 1] - index_base; ++e) {
+                const int64_t r = rowval[e] - index_base;
+                if (r < 0 || r >= k) return fail(LDPCB200_EINVAL, "logical operator index out of range at entry %lld", (long long)e);
+                m[j] ^= 1ull << r;
+            }
+    }
+    h->lmask.swap(m);
+    h->n_logicals = static_cast<int>(k);
+    for (DeviceCtx &d : h->dev) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.set[0].stream));
+        d.lmask.release();
+        if (!h->lmask.empty()) {
+            int rc = d.lmask.reserve(h->lmask.size() * 8);
+            if (rc) return rc;
+            CU(cudaMemcpy(d.lmask.p, h->lmask.data(), h->lmask.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    return 0;
+}
+
+int ldpcb200_score_logical_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_true_err_words,
+                                  const uint32_t *d_err_words, const uint32_t *d_syn_words, unsigned long long *d_out, void *stream)
+{
+    if (!h || dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad handle / dev_slot");
+    if (B <= 0) return 0;
+    if (!d_true_err_words || !d_err_words || !d_syn_words || !d_out) return fail(LDPCB200_EINVAL, "null device buffer");
+    DeviceCtx &d = h->dev[dev_slot];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d.stream;
+    int rc = d.scratch.reserve(static_cast<size_t>(B) * h->SW * 4);
+    if (rc) return rc;
+    bp::score_rows_logical<<<grid_for(B * 32, d.sm_count), 256, 0, st>>>(d.d_colptr, d.d_ve_chk, h->NW, h->SW, B, d_true_err_words, d_err_words,
+                                                                        d_syn_words, d.scratch.as<uint32_t>(),
+                                                                        h->lmask.empty() ? nullptr : d.lmask.as<unsigned long long>(), d_out);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ldpcb200_set_per(ldpcb200_t *h, double per)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (h->variant != LDPCB200_VARIANT_EXACT && !(per > 0.0 && per < 1.0))
+        return fail(LDPCB200_EINVAL, "the log-likelihood-ratio variants need 0 < per < 1 (finite prior)");
+    volatile double one_minus = 1.0 - per;
+    volatile double q = per / one_minus;
+    h->per = per;
+    h->p0 = q;
+    h->regular_p0 = std::isnormal(h->p0) && h->p0 > 0.0;
+    if (h->variant != LDPCB200_VARIANT_EXACT) {
+        volatile double r = one_minus / per;
+        h->p0 = std::log(r);
+        if (h->variant == LDPCB200_VARIANT_FAST32) h->p0 = static_cast<double>(static_cast<float>(h->p0));
+    }
+    return 0;
+}
+
+int ldpcb200_sample_decode_score(ldpcb200_t *h, int64_t shots, int64_t first, uint64_t seed, double per_channel, int32_t osd,
+                                 int64_t *out)
+{
+    if (!h || !out) return fail(LDPCB200_EINVAL, "null argument");
+    memset(out, 0, sizeof(int64_t) * LDPCB200_NUM_HARNESS_COUNTERS);
+    if (shots < 0) return fail(LDPCB200_EINVAL, "negative shot count");
+    if (osd && h->variant != LDPCB200_VARIANT_EXACT) return fail(LDPCB200_EUNSUPPORTED, "OSD-0 is defined on the posterior ratios of the exact variant");
+    if (shots == 0) return 0;
+    int rc = configure(h);
+    if (rc) return rc;
+    const int nd = static_cast<int>(h->dev.size());
+    std::vector<int64_t> lo(nd + 1, 0);
+    const int64_t blocks = (shots + 31) / 32;
+    for (int k = 0; k <= nd; ++k) lo[k] = std::min<int64_t>(shots, (blocks * k / nd) * 32);
+    lo[nd] = shots;
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<int64_t> ctr(static_cast<size_t>(nd) * LDPCB200_NUM_HARNESS_COUNTERS, 0);
+    auto work = [&](int k) {
+        rcs[k] = harness_on_device(h, h->dev[k], first + lo[k], lo[k + 1] - lo[k], seed, per_channel, osd != 0,
+                                   &ctr[static_cast<size_t>(k) * LDPCB200_NUM_HARNESS_COUNTERS]);
+        if (rcs[k]) errs[k] = g_err;
+    };
+    if (nd == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nd; ++k) th.emplace_back(work, k);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < nd; ++k)
+        if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    bool summed = false;
+    if (nd > 1) {
+        nccl_prepare(h);
+        if (h->nccl_state == 1) {                          // one grouped ncclAllReduce of the 8 counters (K7 of SURVEY section 2)
+            rc = nccl_sum_block(h, LDPCB200_NUM_HARNESS_COUNTERS, [](DeviceCtx &d) { return d.hs_ctr.p; }, out);
+            if (rc) return rc;
+            summed = true;
+        }
+    }
+    if (!summed)
+        for (int k = 0; k < nd; ++k)
+            for (int c = 0; c < LDPCB200_NUM_HARNESS_COUNTERS; ++c) out[c] += ctr[static_cast<size_t>(k) * LDPCB200_NUM_HARNESS_COUNTERS + c];
     return 0;
 }
 

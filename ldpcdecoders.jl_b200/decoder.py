@@ -71,7 +71,7 @@ class BeliefPropagationDecoder:
         h = ctypes.c_void_p()
         _lib.check(lib.ldpcb200_create(self.s, self.n, colptr.ctypes.data, rowval.ctypes.data, 0,
                                        self.per, self.max_iters,
-                                       {"exact": _lib.VARIANT_EXACT, "minsum": _lib.VARIANT_MINSUM}[variant],
+                                       {"exact": _lib.VARIANT_EXACT, "minsum": _lib.VARIANT_MINSUM, "fast": _lib.VARIANT_FAST32}[variant],
                                        devs.ctypes.data if devs is not None else None, ndev,
                                        ctypes.byref(h)))
         self._h = h
@@ -92,6 +92,39 @@ class BeliefPropagationDecoder:
         out = ctypes.c_int64()
         _lib.check(self._lib.ldpcb200_launch_count(self._h, ctypes.byref(out)))
         return out.value
+
+    # -- sampling + scoring harness ---------------------------------------
+    def set_logicals(self, L):
+        """Logical operators L (k x n, k <= 64, any 0/1 matrix; None removes them): a decoded error then counts as a
+        failure when it does not reproduce the syndrome or differs from the true error by a logical operator."""
+        if L is None:
+            _lib.check(self._lib.ldpcb200_set_logicals(self._h, 0, None, None, 0))
+            return
+        Lc = sp.csc_matrix(L)
+        Lc.data[:] = Lc.data % 2
+        Lc.eliminate_zeros()
+        Lc.sort_indices()
+        assert Lc.shape[1] == self.n
+        colptr = np.ascontiguousarray(Lc.indptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(Lc.indices, dtype=np.int64)
+        _lib.check(self._lib.ldpcb200_set_logicals(self._h, Lc.shape[0], colptr.ctypes.data, rowval.ctypes.data, 0))
+
+    def set_per(self, per):
+        """New prior (channel_probs) for the same device-resident Tanner graph."""
+        _lib.check(self._lib.ldpcb200_set_per(self._h, float(per)))
+        self.per = float(per)
+
+    def sample_decode_score(self, shots, first, seed, per_channel, osd=False):
+        """`shots` synthetic errors of rate per_channel sampled, decoded and scored on the handle's devices
+        (ldpcb200_sample_decode_score); returns a dict of the eight counters."""
+        out = (ctypes.c_int64 * _lib.NUM_HARNESS_COUNTERS)()
+        _lib.check(self._lib.ldpcb200_sample_decode_score(self._h, int(shots), int(first), ctypes.c_uint64(seed), float(per_channel),
+                                                          1 if osd else 0, out))
+        return dict(zip(_lib.HARNESS_FIELDS, [int(x) for x in out]))
+
+    def score_logical_device(self, B, d_true_err_words, d_err_words, d_syn_words, d_out, stream=None, dev_slot=0):
+        _lib.check(self._lib.ldpcb200_score_logical_device(self._h, dev_slot, int(B), d_true_err_words, d_err_words, d_syn_words,
+                                                           d_out, stream))
 
     def kernel_profile(self, reset=True, dev_slot=0):
         """Per-phase SM cycles of the shared-memory kernel (option kernel_profile=1); see ldpcb200_kernel_profile."""
@@ -251,7 +284,7 @@ def decode_b(decoder, syndrome):
         ratio = np.ones((decoder.n, 1), dtype=np.float64, order="F")
     decoder.last_counters = decoder.decode_raw(1, syn_f, _fmt_of(syn_f, "syndrome"), max(decoder.s, 1), err,
                                                _lib.FMT_F64, max(decoder.n, 1), conv, None, ratio)
-    if ratio is not None and decoder.variant == "minsum":
+    if ratio is not None and decoder.variant in ("minsum", "fast"):
         decoder.scratch.log_probabs[:] = ratio[:, 0]                      # posterior LLR log(P0/P1)
     elif ratio is not None:
         with np.errstate(all="ignore"):
@@ -259,3 +292,24 @@ def decode_b(decoder, syndrome):
     else:
         decoder.scratch.log_probabs[:] = 0.0
     return decoder.scratch.err, bool(conv[0])
+
+
+def ler_curve(decoder, pers, shots, seed=12345, osd=False, match_prior=True):
+    """Logical-error-rate sweep on the GPU (the loop of test/test_bp_decoder.jl:19-30 per error rate, with the batch
+    sampled, decoded and scored on the device): for each physical error rate the prior is set to it (match_prior), `shots`
+    errors are drawn from the Philox stream, decoded (BP, or BP+OSD-0 with osd=True) and compared with the truth.
+    Returns one dict per rate: the eight counters plus ler (= failures / shots), converged_frac and mean_iters."""
+    bp = decoder.bp_decoder if isinstance(decoder, BeliefPropagationOSDDecoder) else decoder
+    osd = osd or isinstance(decoder, BeliefPropagationOSDDecoder)
+    prior = bp.per
+    rows = []
+    for k, per in enumerate(pers):
+        if match_prior:
+            bp.set_per(per)
+        c = bp.sample_decode_score(shots, k * int(shots), seed, per, osd=osd)
+        c.update(per=float(per), ler=c["failures"] / max(c["shots"], 1), converged_frac=c["converged"] / max(c["shots"], 1),
+                 mean_iters=c["iterations"] / max(c["shots"], 1))
+        rows.append(c)
+    if match_prior:
+        bp.set_per(prior)
+    return rows

@@ -212,6 +212,80 @@ static int decode_edge_minsum(const graph_t *g, double per, int max_iters, const
     return converged;
 }
 
+/* Fast FP32 variant (LDPCB200_VARIANT_FAST32).  NOT a restatement of the BP decoder -- the reference's BP decoder works in the
+ * ratio domain in Float64 -- but the definition the CUDA fast kernels are compared with: the clamped tanh/atanh check update
+ * of the only LLR-domain BP in the package (src/decoders/bpots_decoder.jl:182-211: tanh(nu/2) clamped to +-0.99999, product
+ * clamped to +-0.99999, 2 atanh) on the BP decoder's flooding schedule, priors log((1-per)/per), early stop and tie rule, all
+ * in float.  tanh(L/2) = (1-u)/(1+u), u = 2^(-|L| log2 e); 2 atanh(x) = ln 2 * log2((1+x)/(1-x)).  The kernels evaluate
+ * 2^x, 1/x and log2 x with the GPU's special-function unit, so agreement is statistical (the tests bound it), not bitwise. */
+static float fast_tanh_half(float L)
+{
+    float u = exp2f(-fabsf(L) * 1.4426950408889634f);
+    float t = (1.0f - u) / (1.0f + u);
+    if (t > 0.99999f) t = 0.99999f;
+    return copysignf(t, L);
+}
+static float fast_two_atanh(float x)
+{
+    if (x > 0.99999f) x = 0.99999f;
+    if (x < -0.99999f) x = -0.99999f;
+    return log2f((1.0f + x) / (1.0f - x)) * 0.6931471805599453f;
+}
+
+static int decode_edge_fast32(const graph_t *g, double per, int max_iters, const uint8_t *syn,
+                              double *b2c_d, double *c2b_d, uint8_t *err, double *ratio, int32_t *iters_out)
+{
+    const int64_t s = g->s, n = g->n;
+    float *b2c = (float *)b2c_d, *c2b = (float *)c2b_d;         /* the double buffers are large enough */
+    volatile double one_minus = 1.0 - per;
+    volatile double r = one_minus / per;
+    const float L0 = (float)log(r);
+    float t[128], S[128];
+    memset(err, 0, (size_t)n);
+    if (ratio) for (int64_t j = 0; j < n; ++j) ratio[j] = 0.0;
+    for (int64_t e = 0; e < g->E; ++e) b2c[e] = L0;
+    int converged = 0;
+    int32_t it = 0;
+    for (int iter = 1; iter <= max_iters; ++iter) {
+        it = iter;
+        for (int64_t i = 0; i < s; ++i) {
+            const int64_t r0 = g->rowptr[i], d = g->rowptr[i + 1] - r0;
+            if (d == 0) continue;
+            for (int64_t k = 0; k < d; ++k) t[k] = fast_tanh_half(b2c[g->rowedge[r0 + k]]);
+            S[d - 1] = 1.0f;
+            for (int64_t k = d - 2; k >= 0; --k) S[k] = S[k + 1] * t[k + 1];
+            float P = syn[i] ? -1.0f : 1.0f;
+            for (int64_t k = 0; k < d; ++k) {
+                c2b[g->rowedge[r0 + k]] = fast_two_atanh(P * S[k]);
+                P *= t[k];
+            }
+        }
+        for (int64_t j = 0; j < n; ++j) {
+            float run = L0;
+            for (int64_t e = g->colptr[j]; e < g->colptr[j + 1]; ++e) {
+                b2c[e] = run;
+                run = run + c2b[e];
+            }
+            if (ratio) ratio[j] = (double)run;
+            err[j] = (run <= 0) ? 1 : 0;
+            float U = 0.0f;
+            for (int64_t e = g->colptr[j + 1] - 1; e >= g->colptr[j]; --e) {
+                b2c[e] = b2c[e] + U;
+                U = U + c2b[e];
+            }
+        }
+        int ok = 1;
+        for (int64_t i = 0; i < s && ok; ++i) {
+            unsigned par = 0;
+            for (int64_t k = g->rowptr[i]; k < g->rowptr[i + 1]; ++k) par ^= err[g->rowvar[k]];
+            if (par != (unsigned)syn[i]) ok = 0;
+        }
+        if (ok) { converged = 1; break; }
+    }
+    if (iters_out) *iters_out = (max_iters > 0) ? it : 0;
+    return converged;
+}
+
 /* One decode!, dense "faithful cost" storage: two s*n column-major matrices exactly like
  * BeliefPropagationScratchSpace (belief_propagation.jl:3-22), full reset per call (:83-91),
  * and the allocating mat-vec of :180-181. */
@@ -300,7 +374,7 @@ int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
                     const uint8_t *syn, uint8_t *err, uint8_t *conv,
                     int32_t *iters, double *ratio, int32_t nthreads, int32_t dense)
 {
-    /* dense: 0 = edge-indexed, 1 = dense faithful cost, 2 = min-sum variant (edge-indexed) */
+    /* dense: 0 = edge-indexed, 1 = dense faithful cost, 2 = min-sum variant (edge-indexed), 3 = fast FP32 variant */
     graph_t g;
     int rc = build_graph(&g, s, n, colptr, rowval);
     if (rc) return rc;
@@ -334,6 +408,7 @@ int bp_oracle_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *
                 int32_t itc = 0;
                 int cv = (dense == 1) ? decode_dense(&g, per, max_iters, sc, a, b, errd, chan, logp, ec, rc_, &itc)
                        : (dense == 2) ? decode_edge_minsum(&g, per, max_iters, sc, a, b, ec, rc_, &itc)
+                       : (dense == 3) ? decode_edge_fast32(&g, per, max_iters, sc, a, b, ec, rc_, &itc)
                                       : decode_edge(&g, per, max_iters, sc, a, b, ec, rc_, &itc);
                 conv[c] = (uint8_t)cv;
                 if (iters) iters[c] = itc;

@@ -95,7 +95,7 @@ def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_rat
                              _p(err, ctypes.c_uint8), _p(conv, ctypes.c_uint8),
                              _p(iters, ctypes.c_int32),
                              _p(ratio, ctypes.c_double) if want_ratio else None,
-                             int(nthreads), 2 if variant == "minsum" else (1 if dense else 0))
+                             int(nthreads), {"minsum": 2, "fast": 3}.get(variant, 1 if dense else 0))
     if rc != 0:
         raise RuntimeError("bp_oracle_batch failed: %d" % rc)
     out = dict(errors=err, converged=conv.astype(bool), iters=iters)

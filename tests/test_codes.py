@@ -31,3 +31,18 @@ def test_surface_weights(codes):
     H = codes.surface_x(15)
     rs = np.asarray(H.sum(1)).ravel()
     assert sorted(np.unique(rs)) == [2, 4] and (rs == 2).sum() == 14 and (rs == 4).sum() == 98
+
+
+def test_css_logicals_of_surface_and_gross_codes(codes):
+    """Logical operators used for failure counting: commute with the other check type, independent of the stabilizers,
+    and as many as the code has logical qubits (surface: 1, gross: 12)."""
+    import numpy as np
+    for Hx, Hz, k in ((codes.surface_x(5), codes.surface_z(5), 1), (codes.gross_x(), codes.gross_z(), 12)):
+        assert ((Hx @ Hz.T).toarray() % 2 == 0).all()
+        L = codes.css_logicals(Hx, Hz)
+        assert L.shape == (k, Hx.shape[1])
+        assert ((Hz @ L.T).toarray() % 2 == 0).all()
+        # a stabilizer (row of Hz) is harmless, a logical operator of the other type is not
+        assert ((L @ Hz.T).toarray() % 2 == 0).all()
+        Lz = codes.css_logicals(Hz, Hx)
+        assert np.linalg.matrix_rank((L @ Lz.T).toarray() % 2) >= 1
