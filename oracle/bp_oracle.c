@@ -504,6 +504,13 @@ int bp_oracle_num_threads(void)
  * ------------------------------------------------------------------------------------ */
 typedef struct { double key; int64_t idx; } keyidx_t;
 
+/* Sort key of the reliability order: 0 (default, what the CUDA kernel computes) r = RN(1/R); 1 r = exp(log(1/R)) with this
+ * libm's exp/log -- the reference's own expression exp.(log_probabs), log_probabs = log(1/R) (belief_propagation.jl:163,
+ * belief_propagation_osd.jl:53), evaluated with glibc instead of Julia's exp/log.  Mode 1 exists to MEASURE how often the
+ * composition changes the order (tools/osd_key_study.py): it is not bit-identical to Julia either. */
+static int g_osd_key_mode = 0;
+void bp_oracle_set_osd_key_mode(int m) { g_osd_key_mode = m; }
+
 static int cmp_keyidx_desc(const void *a, const void *b)
 {
     const keyidx_t *x = (const keyidx_t *)a, *y = (const keyidx_t *)b;
@@ -523,6 +530,7 @@ static int osd0_one(const graph_t *g, const int64_t *colptr, const int64_t *rowv
     /* :53-55  reliability order */
     for (int64_t j = 0; j < n; ++j) {
         double r = 1.0 / ratio[j];
+        if (g_osd_key_mode == 1) r = exp(log(r));
         double q = 1.0 - r;
         ki[j].key = (r > q) ? r : q;
         ki[j].idx = j;

@@ -51,6 +51,8 @@ def load():
                                           ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
     lib.bp_oracle_set_minsum_scale.argtypes = [ctypes.c_double]
     lib.bp_oracle_set_minsum_scale.restype = None
+    lib.bp_oracle_set_osd_key_mode.argtypes = [ctypes.c_int]
+    lib.bp_oracle_set_osd_key_mode.restype = None
     lib.bp_oracle_threshold.restype = ctypes.c_uint32
     lib.bp_oracle_threshold.argtypes = [ctypes.c_double]
     lib.bp_oracle_num_threads.restype = ctypes.c_int
@@ -104,11 +106,14 @@ def batch_decode(H, per, max_iters, syndromes, nthreads=1, dense=False, want_rat
     return out
 
 
-def bposd_decode(H, per, max_iters, syndromes, nthreads=1):
+def bposd_decode(H, per, max_iters, syndromes, nthreads=1, key_mode=0):
     """Restated decode!(::BeliefPropagationOSDDecoder, syndrome) with osd_order = 0
     (belief_propagation_osd.jl:49-125) applied to every column.  Returns dict(errors (n,B) uint8 -- the
-    OSD result, converged (B,) bool -- BP's flag, bp_errors (n,B) uint8, pivots (B,) int32)."""
+    OSD result, converged (B,) bool -- BP's flag, bp_errors (n,B) uint8, pivots (B,) int32).
+    key_mode: 0 = sort key from RN(1/R) (what the kernel computes), 1 = from exp(log(1/R)) with libm (the reference's
+    expression; used to measure the stated deviation)."""
     lib = load()
+    lib.bp_oracle_set_osd_key_mode(int(key_mode))
     s, n, colptr, rowval = csc_arrays(H)
     syn = np.asfortranarray(np.asarray(syndromes).astype(np.uint8))
     if syn.ndim == 1:

@@ -32,11 +32,31 @@ def main():
                             rowval=Hc.indices.astype(np.int64), per=per, max_iters=mi, syndromes=syn,
                             errors=r["errors"], converged=r["converged"], iters=r["iters"],
                             ratio_bits=r["ratio"].view(np.uint64))
-        if H.shape[1] <= 300:      # text twins for the Julia cross-check (small codes only)
+        if H.shape[1] <= 300:      # dense text twins (small codes only; kept for older readers of this directory)
             np.savetxt(os.path.join(HERE, name + ".H.txt"), H.toarray().astype(int), fmt="%d")
             np.savetxt(os.path.join(HERE, name + ".syndromes.txt"), syn.astype(int), fmt="%d")
             np.savetxt(os.path.join(HERE, name + ".meta.txt"), np.array([per, mi]))
-        print(name, H.shape, "converged", r["converged"].mean(), "mean iters", r["iters"].mean())
+        # text twins for oracle/dump_golden.jl (every case; H as 1-based "row col" pairs): inputs AND the oracle's outputs,
+        # so that the Julia script can compare the real package with them and fail loudly
+        tdir = os.path.join(HERE, "julia_twins")
+        os.makedirs(tdir, exist_ok=True)
+        coo = H.tocoo()
+        np.savetxt(os.path.join(tdir, name + ".H.coo.txt"), np.stack([coo.row + 1, coo.col + 1], axis=1), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".meta.txt"), np.array([[H.shape[0], H.shape[1], per, mi]]), fmt="%.17g")
+        np.savetxt(os.path.join(tdir, name + ".syndromes.txt"), syn.astype(int), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".errors.txt"), r["errors"].astype(int), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".converged.txt"), r["converged"].astype(int), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".iters.txt"), r["iters"].astype(int), fmt="%d")
+        # BP + OSD-0 on the same syndromes with a short iteration budget, so that many of them reach the OSD stage
+        mi_osd = 6
+        ro = oracle.bposd_decode(H, per, mi_osd, syn)
+        np.savetxt(os.path.join(tdir, name + ".osd_meta.txt"), np.array([[mi_osd, int((~ro["converged"]).sum())]]), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".osd_errors.txt"), ro["errors"].astype(int), fmt="%d")
+        np.savetxt(os.path.join(tdir, name + ".osd_converged.txt"), ro["converged"].astype(int), fmt="%d")
+        np.savez_compressed(os.path.join(HERE, name + ".osd.npz"), max_iters=mi_osd, errors=ro["errors"], converged=ro["converged"],
+                            pivots=ro["pivots"])
+        print(name, H.shape, "converged", r["converged"].mean(), "mean iters", r["iters"].mean(), "| OSD case: unconverged",
+              int((~ro["converged"]).sum()), "of", B)
 
 
 if __name__ == "__main__":

@@ -322,7 +322,7 @@ def test_forced_iterations_mode_runs_max_iters(pkg, oracle, codes):
 GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("fixture", sorted(f for f in __import__("os").listdir(GOLDEN) if f.endswith(".npz")))
+@pytest.mark.parametrize("fixture", sorted(f for f in __import__("os").listdir(GOLDEN) if f.endswith(".npz") and not f.endswith(".osd.npz")))
 def test_golden_fixtures_on_gpu(pkg, fixture):
     """The committed fixtures (tests/golden/make_golden.py) decoded by the CUDA path."""
     z = np.load(__import__("os").path.join(GOLDEN, fixture))
@@ -861,3 +861,14 @@ def test_fast32_quality_is_close_to_exact(pkg, oracle, codes):
     small = run_gpu_variant(pkg, H, 0.03, mi, syn[:, :100], "fast")          # node-parallel kernel (B <= SM count)
     pers = run_gpu_variant(pkg, H, 0.03, mi, syn[:, :100], "fast", small_batch=0)
     assert np.array_equal(small["errors"], pers["errors"]) and np.array_equal(small["iters"], pers["iters"])
+
+
+@pytest.mark.parametrize("name", ["gross_p05", "surface15_p03", "hgp_p05", "gallager1000_p03"])
+def test_golden_osd_fixtures_on_gpu(pkg, name):
+    """The committed BP+OSD-0 fixtures (what oracle/dump_golden.jl compares the real package with) through the CUDA path."""
+    z = np.load(__import__("os").path.join(GOLDEN, name + ".npz"))
+    zo = np.load(__import__("os").path.join(GOLDEN, name + ".osd.npz"))
+    H = sp.csc_matrix((np.ones(len(z["rowval"]), dtype=np.uint8), z["rowval"], z["colptr"]), shape=tuple(z["shape"]))
+    g = run_gpu_bposd(pkg, H, float(z["per"]), int(zo["max_iters"]), z["syndromes"])
+    assert np.array_equal(g["errors"], zo["errors"]) and np.array_equal(g["converged"], zo["converged"])
+    assert g["stats"][0] == int((~zo["converged"]).sum()) and g["stats"][1] == int(zo["pivots"][~zo["converged"]].sum())

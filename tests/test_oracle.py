@@ -141,7 +141,7 @@ def test_sampler_is_shard_independent(oracle, codes):
     assert abs(e_all.mean() - 0.05) < 0.01
 
 
-@pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz")) if os.path.isdir(GOLDEN) else [])
+@pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.endswith(".osd.npz")) if os.path.isdir(GOLDEN) else [])
 def test_golden_fixtures(oracle, fixture):
     """Regression pins generated by tests/golden/make_golden.py (oracle outputs, NOT reference
     outputs -- Julia cannot run here; see the PARITY UNPINNED note in oracle/bp_oracle.c)."""
@@ -222,3 +222,26 @@ def test_osd0_reference_testset_properties(oracle, codes):
     assert np.array_equal((Hd @ out["errors"].astype(np.int64)) % 2, syn.astype(np.int64))
     bp_ok = ((Hd @ out["bp_errors"].astype(np.int64)) % 2 == syn).all(axis=0)
     assert np.array_equal(bp_ok, out["converged"])
+
+
+@pytest.mark.parametrize("name", ["gross_p05", "surface15_p03", "hgp_p05", "gallager1000_p03"])
+def test_golden_osd_fixtures_and_julia_twins(oracle, name):
+    """BP+OSD-0 fixtures (restated reference, belief_propagation_osd.jl:49-125) and the text twins that
+    oracle/dump_golden.jl feeds to the real package: the twins must say exactly what the .npz files say."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    zo = np.load(os.path.join(GOLDEN, name + ".osd.npz"))
+    H = sp.csc_matrix((np.ones(len(z["rowval"]), dtype=np.uint8), z["rowval"], z["colptr"]), shape=tuple(z["shape"]))
+    r = oracle.bposd_decode(H, float(z["per"]), int(zo["max_iters"]), z["syndromes"])
+    assert np.array_equal(r["errors"], zo["errors"]) and np.array_equal(r["converged"], zo["converged"])
+    assert np.array_equal(r["pivots"], zo["pivots"])
+    t = os.path.join(GOLDEN, "julia_twins", name)
+    ij = np.loadtxt(t + ".H.coo.txt", dtype=np.int64).reshape(-1, 2)
+    meta = np.loadtxt(t + ".meta.txt")
+    Ht = sp.csc_matrix((np.ones(len(ij), dtype=np.uint8), (ij[:, 0] - 1, ij[:, 1] - 1)), shape=(int(meta[0]), int(meta[1])))
+    assert (Ht != H).nnz == 0 and meta[2] == float(z["per"]) and int(meta[3]) == int(z["max_iters"])
+    ld = lambda suffix: np.loadtxt(t + suffix, dtype=np.int64, ndmin=2)
+    assert np.array_equal(ld(".syndromes.txt"), z["syndromes"])
+    assert np.array_equal(ld(".errors.txt"), z["errors"]) and np.array_equal(ld(".converged.txt").ravel(), z["converged"].astype(int))
+    assert np.array_equal(ld(".iters.txt").ravel(), z["iters"])
+    assert np.array_equal(ld(".osd_errors.txt"), zo["errors"]) and np.array_equal(ld(".osd_converged.txt").ravel(), zo["converged"].astype(int))
+    assert int(ld(".osd_meta.txt").ravel()[0]) == int(zo["max_iters"])
