@@ -117,6 +117,9 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   outputs are then those of the last iteration), "chunk" (syndromes per host<->device chunk),
  *   "small_batch" (batches of at most this many syndromes run on the node-parallel kernel, one CTA per syndrome:
  *   the low-latency path of decode!; -1 = number of SMs (default), 0 = never),
+ *   "osd_order" (ldpcb200_bposd_decode_batch and the sampling harness: 0 (default) = OSD-0 on the syndromes BP left
+ *   unconverged; 1..12 = the order-O exhaustive search of belief_propagation_osd.jl:127-209 on EVERY syndrome, as the
+ *   reference's decode! does for osd_order > 0),
  *   "ratio_last_only" (ldpcb200_decode_device writes d_posterior_ratio only in iteration max_iters: all an OSD
  *   stage needs, since it only reads the ratios of syndromes that did not converge; default 0). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);
@@ -151,7 +154,8 @@ int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B,
 /* Replaces decode!(::BeliefPropagationOSDDecoder, syndrome) with osd_order = 0
  * (src/decoders/belief_propagation_osd.jl:49-61, osd(..., Val(0)) :63-125), applied to every column of a
  * batch: BP as ldpcb200_decode_batch, then OSD-0 on the syndromes BP left unconverged (the reference returns
- * BP's own decision for the converged ones, :72-74).  errors receives the OSD result, converged BP's flag
+ * BP's own decision for the converged ones, :72-74); with option "osd_order" = O > 0, osd(..., Val{O}) (:127-209) on every
+ * column instead.  errors receives the OSD result, converged BP's flag
  * (:60 returns BP's `converged`).  osd_stats: nullable, LDPCB200_NUM_OSD_STATS int64.  Exact variant only;
  * the bit-packed s x (n+1) matrix must fit in shared memory (LDPCB200_EUNSUPPORTED otherwise).
  * Sort key: max(r, 1-r) with r = RN(1/R_j) where the reference has exp(log(1/R_j)). */

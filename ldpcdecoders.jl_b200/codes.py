@@ -39,6 +39,38 @@ def gallager(n, wr, wc, seed=0):
     return _csc(np.concatenate(rows), np.concatenate(cols), (block * wc, n))
 
 
+def parity_check_matrix(n, wr, wc, seed=0):
+    """parity_check_matrix(n, wr, wc) of /root/reference/src/parity_generator.jl:21-45 (same ensemble, seeded)."""
+    return gallager(n, wr, wc, seed=seed)
+
+
+def save_pcm(H, file_path):
+    """save_pcm(H, file_path) (parity_generator.jl:47-49): the matrix as 0/1 integers, one row per line, tab separated --
+    the text Julia's writedlm(file_path, Int.(H)) produces, so files travel between the two packages."""
+    A = np.asarray(sp.csc_matrix(H).todense()).astype(np.int64) & 1
+    with open(file_path, "w") as f:
+        for row in A:
+            f.write("\t".join("1" if x else "0" for x in row) + "\n")
+
+
+def load_pcm(file_path):
+    """load_pcm(file_path) (parity_generator.jl:51-54): reads what save_pcm / Julia's writedlm wrote (any whitespace or comma
+    delimiter, integer or float spelling of 0/1) and returns it as a sparse 0/1 matrix (the reference returns Int.(H))."""
+    rows = []
+    with open(file_path) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            rows.append([int(float(tok)) for tok in line.replace(",", " ").split()])
+    A = np.array(rows, dtype=np.int64)
+    if A.ndim != 2:
+        raise ValueError("ragged parity-check file")
+    if ((A != 0) & (A != 1)).any():
+        raise ValueError("parity-check entries must be 0 or 1")
+    return sp.csc_matrix(A.astype(np.uint8))
+
+
 def surface_x(d):
     """X checks of the rotated surface code: ((d*d-1)/2) x (d*d); bulk weight 4, boundary 2."""
     rows, cols = [], []

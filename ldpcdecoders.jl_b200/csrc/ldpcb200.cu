@@ -186,6 +186,7 @@ struct ldpcb200 {
     int tables_cv_warps = 0;             // layout the device copies of `tables` currently have
     bool tables_dirty = false;           // host blob rebuilt, device copies stale
     int opt_cv = 1;                      // bp_smem_kernel: contiguous variable ownership where the code allows it
+    int opt_osd_order = 0;               // ldpcb200_bposd_decode_batch / the harness: OSD order (0: OSD-0 on the unconverged syndromes)
     int opt_stage_pageable = 1;          // host batches: stage pageable caller memory through pinned blocks (0: copy it directly)
     // options
     int opt_family = LDPCB200_FAMILY_AUTO, opt_warps = 0, opt_slots = 0, opt_early_stop = 1;
@@ -897,7 +898,7 @@ int osd_layout(const ldpcb200 *h, bp::OsdParams &p)
     off = (off + 15) / 16 * 16;
     p.off_key = static_cast<int>(off); off += static_cast<long long>(np) * 8;
     p.off_idx = static_cast<int>(off); off += static_cast<long long>(np) * 4;
-    p.off_piv = static_cast<int>(off); off += static_cast<long long>(std::max(m, 1)) * 4 * 5;   // piv, prow, pcol, list, rowat
+    p.off_piv = static_cast<int>(off); off += static_cast<long long>(std::max(m, 1)) * 4 * 5 + static_cast<long long>(p.NWr) * 4;   // piv, prow, pcol, list, rowat (+ the order-O kernel's error words)
     p.off_red = static_cast<int>(off); off += (16 + 192 + p.NWr / 4 + 1) * 4;
     return off > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(off);
 }
@@ -947,6 +948,42 @@ int osd0_on_device(ldpcb200 *h, DeviceCtx &d, DeviceCtx::StageSet &S, int64_t B,
         default: CU(launch(bp::osd0_kernel<kOsdThreads, 8>)); break;
     }
     h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- OSD of order O > 0 on EVERY syndrome of the batch (osd.cuh: osdk_kernel); err_words: BP decisions in, OSD result out.
+int osdk_on_device(ldpcb200 *h, DeviceCtx &d, DeviceCtx::StageSet &S, int64_t B, int order, const uint32_t *syn_words,
+                   uint32_t *err_words, const double *ratio, unsigned long long *stats, cudaStream_t st)
+{
+    if (B <= 0) return 0;
+    if (h->variant != LDPCB200_VARIANT_EXACT)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD is defined on the posterior ratios of the exact variant");
+    if (order < 1 || order > bp::kOsdMaxOrder) return fail(LDPCB200_EUNSUPPORTED, "osd_order must be between 0 and %d", bp::kOsdMaxOrder);
+    if (B > 0x7fffffffLL) return fail(LDPCB200_EINVAL, "OSD: at most 2^31-1 syndromes per call");
+    CU(cudaSetDevice(d.device));
+    bp::OsdParams p{};
+    const int smem = osd_layout(h, p);
+    if (smem > d.smem_optin)
+        return fail(LDPCB200_EUNSUPPORTED, "OSD: the bit-packed %lld x %lld matrix (%d bytes) does not fit in shared memory",
+                    static_cast<long long>(h->s), static_cast<long long>(h->n), smem);
+    int rc;
+    if ((rc = S.osd_ctl.reserve(16))) return rc;
+    if (!stats) {
+        if ((rc = d.osd_stats.reserve(64))) return rc;
+        stats = d.osd_stats.as<unsigned long long>();
+    }
+    CU(cudaMemsetAsync(S.osd_ctl.p, 0, 16, st));
+    p.colptr = d.d_colptr; p.rowval = d.d_ve_chk;
+    p.syn_words = syn_words; p.err_words = err_words; p.ratio = ratio;
+    p.list = nullptr; p.count = nullptr; p.queue = S.osd_ctl.as<int>() + 1;
+    p.stats = stats;
+    const int per_sm = std::max(1, std::min(4, d.smem_per_sm / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(d.sm_count) * per_sm));
+    auto kern = bp::osdk_kernel<kOsdThreads>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kOsdThreads, smem, st>>>(p, order, B);
+    h->launches++;
     CU(cudaGetLastError());
     return 0;
 }
@@ -1196,9 +1233,11 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         }
         // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
         if (have_prev_decode) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
+        // (OSD-0 only reads the ratios of unconverged syndromes: those of iteration max_iters; a higher order post-processes
+        //  every syndrome, so the ratios of each syndrome's own last iteration are needed)
         rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
                               (ratio || (osd && h->max_iters > 0)) ? S.ratio.as<double>() : nullptr,
-                              d.counters.as<unsigned long long>(), st, osd && !ratio);
+                              d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0);
         if (rc) return rc;
         CU(cudaEventRecord(d.decode_done, st));
         have_prev_decode = true;
@@ -1207,8 +1246,12 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
                 bp::osd_fill_ones_kernel<<<grid_for(Bc * n, d.sm_count), 256, 0, st>>>(S.ratio.as<double>(), Bc * n);
                 h->launches++;
             }
-            rc = osd0_on_device(h, d, S, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.ratio.as<double>(),
-                                d.osd_stats.as<unsigned long long>(), st);
+            if (h->opt_osd_order > 0)
+                rc = osdk_on_device(h, d, S, Bc, h->opt_osd_order, syn_words, S.err_words.as<uint32_t>(), S.ratio.as<double>(),
+                                    d.osd_stats.as<unsigned long long>(), st);
+            else
+                rc = osd0_on_device(h, d, S, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.ratio.as<double>(),
+                                    d.osd_stats.as<unsigned long long>(), st);
             if (rc) return rc;
         }
         // ---- packed rows -> caller's format -> host
@@ -1368,15 +1411,19 @@ int harness_on_device(ldpcb200 *h, DeviceCtx &d, int64_t first, int64_t shots, u
             h->launches += 2;
             const bool want_ratio = osd && h->max_iters > 0;
             rc = decode_on_device(h, d, bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(), d.hs_iters.as<int32_t>(),
-                                  want_ratio ? d.hs_ratio.as<double>() : nullptr, ctr, st, true);
+                                  want_ratio ? d.hs_ratio.as<double>() : nullptr, ctr, st, h->opt_osd_order == 0);
             if (rc) return rc;
             if (osd) {
                 if (h->max_iters <= 0) {
                     bp::osd_fill_ones_kernel<<<grid_for(bt * h->n, d.sm_count), 256, 0, st>>>(d.hs_ratio.as<double>(), bt * h->n);
                     h->launches++;
                 }
-                rc = osd0_on_device(h, d, d.set[0], bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(),
-                                    d.hs_ratio.as<double>(), d.osd_stats.as<unsigned long long>(), st);
+                if (h->opt_osd_order > 0)
+                    rc = osdk_on_device(h, d, d.set[0], bt, h->opt_osd_order, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(),
+                                        d.hs_ratio.as<double>(), d.osd_stats.as<unsigned long long>(), st);
+                else
+                    rc = osd0_on_device(h, d, d.set[0], bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(),
+                                        d.hs_ratio.as<double>(), d.osd_stats.as<unsigned long long>(), st);
                 if (rc) return rc;
             }
             bp::score_rows_logical<<<grid_for(bt * 32, d.sm_count), 256, 0, st>>>(
@@ -1486,6 +1533,11 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (!h || !key) return fail(LDPCB200_EINVAL, "null handle or key");
     const std::string k(key);
     if (k == "small_batch") { h->opt_small_batch = value; return 0; }
+    if (k == "osd_order") {
+        if (value < 0 || value > bp::kOsdMaxOrder) return fail(LDPCB200_EUNSUPPORTED, "osd_order must be between 0 and %d", bp::kOsdMaxOrder);
+        h->opt_osd_order = static_cast<int>(value);
+        return 0;
+    }
     if (k == "stage_pageable") { h->opt_stage_pageable = value ? 1 : 0; return 0; }
     if (k == "nccl") { h->opt_nccl = value ? 1 : 0; return 0; }      // before the first multi-device batch
     if (k == "osd_profile") { h->opt_osd_profile = value ? 1 : 0; return 0; }

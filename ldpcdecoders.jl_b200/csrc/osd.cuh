@@ -293,4 +293,210 @@ __global__ void __launch_bounds__(T, 1) osd0_kernel(const OsdParams p)
     }
 }
 
+
+// ---- OSD of order O > 0: osd(H_sorted, syndrome, bp_err_sorted, Val{O}) of
+// /root/reference/src/decoders/belief_propagation_osd.jl:127-209 behind the sort of :53-57 and the un-permutation of :60.
+// decode! applies it to EVERY syndrome (no shortcut for converged ones), so the kernel takes all B columns.
+//   1. reliability sort and bit-packed [H_sorted | syndrome] in shared memory, as in osd0_kernel;
+//   2. Gauss-Jordan: forward elimination in the reference's PHYSICAL row order (position -> row table instead of moving
+//      rows: `findfirst(H[i:end, j])` is the smallest position >= i whose row has bit j, :140-146), then the
+//      back-elimination over the pivots in reverse (:163-170).  Pivot q stands at position q;
+//   3. the exhaustive search (:182-206): with E the bp_err bits on the non-pivot columns, a pivot row q gives
+//      err[pivot col] = s_q xor <row_q, E>; only the first O non-pivot columns change between trials, so per pivot one
+//      precomputed bit a_q (everything but the trial columns) and an O-bit mask b_q (the row on the trial columns) make a
+//      trial a parity of b_q & x.  Trial x = 0 keeps bp_err's own bits on the trial columns (the reference only writes
+//      them for x != 0); weights are compared with `<` in ascending x, so the smallest x among the lightest wins.
+// One CTA per syndrome; O <= kOsdMaxOrder.
+constexpr int kOsdMaxOrder = 12;
+
+template <int T>
+__global__ void __launch_bounds__(T, 1) osdk_kernel(const OsdParams p, const int order_req, const long long B)
+{
+    extern __shared__ __align__(16) unsigned char osd_smem[];
+    uint32_t *Hs = reinterpret_cast<uint32_t *>(osd_smem);
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(osd_smem + p.off_key);
+    int *idx = reinterpret_cast<int *>(osd_smem + p.off_idx);
+    int *piv_r = reinterpret_cast<int *>(osd_smem + p.off_piv);        // [m] row of the q-th pivot
+    int *piv_c = piv_r + p.m;                                          // [m] sorted column of the q-th pivot
+    int *rowat = piv_r + 2 * p.m;                                      // [m] row standing at a position
+    uint32_t *ab = reinterpret_cast<uint32_t *>(piv_r + 3 * p.m);      // [m] a_q | b_q << 1
+    uint32_t *ev = reinterpret_cast<uint32_t *>(piv_r + 4 * p.m);      // [NWr] bp_err over the sorted positions (then: the answer)
+    int *ctl = reinterpret_cast<int *>(osd_smem + p.off_red);          // [16] control words, [16..] per-warp scratch
+    __shared__ int s_work;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = p.m, n = p.n, NWr = p.NWr, NP = p.NP;
+    const int augw = NWr - 1;
+    const uint32_t augm = 0x80000000u;
+    constexpr int NWARP = T / 32;
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(p.queue, 1);
+        __syncthreads();
+        const long long b = s_work;
+        if (b >= B) break;
+        const double *R = p.ratio + b * n;
+        uint32_t *erow = p.err_words + b * p.NW;
+        const uint32_t *srow = p.syn_words + b * p.SW;
+        // ---- reliability keys and stable descending sort (:53-55), as osd0_kernel
+        for (int j = tid; j < NP; j += T) {
+            unsigned long long kb = ~0ull;
+            if (j < n) {
+                const double r = __ddiv_rn(1.0, R[j]);
+                const double q = __dsub_rn(1.0, r);
+                kb = ~static_cast<unsigned long long>(__double_as_longlong(r > q ? r : q));
+            }
+            key[j] = kb;
+            idx[j] = j;
+        }
+        for (int i = tid; i < m * (NWr / 4); i += T) reinterpret_cast<uint4 *>(Hs)[i] = make_uint4(0, 0, 0, 0);
+        for (int r = tid; r < m; r += T) rowat[r] = r;
+        for (int w = tid; w < NWr; w += T) ev[w] = 0u;
+        __syncthreads();
+        for (int k = 2; k <= NP; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int q = tid; q < NP / 2; q += T) {
+                    const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), x = i | j;
+                    const unsigned long long ka = key[i], kb = key[x];
+                    const int ia = idx[i], ib = idx[x];
+                    const bool gt = ka > kb || (ka == kb && ia > ib);
+                    if (gt == ((i & k) == 0)) {
+                        key[i] = kb; key[x] = ka;
+                        idx[i] = ib; idx[x] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- [H_sorted | syndrome] (:56, :137) and bp_err over the sorted positions (:57)
+        for (int r = tid; r < m; r += T)
+            if ((srow[r >> 5] >> (r & 31)) & 1u) atomicOr(&Hs[r * NWr + augw], augm);
+        for (int q = tid; q < n; q += T) {
+            const int c = idx[q];
+            if ((erow[c >> 5] >> (c & 31)) & 1u) atomicOr(&ev[q >> 5], 1u << (q & 31));
+            const uint32_t bit = 1u << (q & 31);
+            const int wq = q >> 5;
+            for (int e = p.colptr[c]; e < p.colptr[c + 1]; ++e) atomicOr(&Hs[p.rowval[e] * NWr + wq], bit);
+        }
+        __syncthreads();
+        // ---- forward elimination (:139-160)
+        int np = 0;
+        for (int j = 0; j < n && np < m; ++j) {
+            const int wj = j >> 5;
+            const uint32_t bj = 1u << (j & 31);
+            int cand = 0x7fffffff;                         // smallest position >= np whose row has bit j
+            for (int pos = np + tid; pos < m; pos += T)
+                if (Hs[rowat[pos] * NWr + wj] & bj) { cand = pos; break; }
+            cand = __reduce_min_sync(0xffffffffu, cand);
+            int *wb = ctl + 16 + (j & 1) * NWARP;
+            if (lane == 0) wb[warp] = cand;
+            __syncthreads();
+            int best = lane < NWARP ? wb[lane] : 0x7fffffff;
+            best = __reduce_min_sync(0xffffffffu, best);
+            if (best == 0x7fffffff) continue;              // :142 no pivot in this column
+            const int pr = rowat[best], other = rowat[np];
+            __syncthreads();                               // everybody has read rowat[best], rowat[np]
+            if (tid == 0) { rowat[np] = pr; rowat[best] = other; piv_r[np] = pr; piv_c[np] = j; }   // :144-148 the swap
+            __syncthreads();
+            const uint32_t *prow = Hs + pr * NWr;
+            for (int pos = np + 1 + tid; pos < m; pos += T) {                                        // :149-154
+                uint32_t *row = Hs + rowat[pos] * NWr;
+                if (row[wj] & bj)
+                    for (int w = wj; w < NWr; ++w) row[w] ^= prow[w];
+            }
+            ++np;
+            __syncthreads();
+        }
+        // ---- back-elimination over the pivots in reverse (:163-170): pivot q stands at position q
+        for (int q = np - 1; q > 0; --q) {
+            const int pj = piv_c[q], wj = pj >> 5;
+            const uint32_t bj = 1u << (pj & 31);
+            const uint32_t *prow = Hs + piv_r[q] * NWr;
+            for (int qq = tid; qq < q; qq += T) {
+                uint32_t *row = Hs + piv_r[qq] * NWr;
+                if (row[wj] & bj)
+                    for (int w = wj; w < NWr; ++w) row[w] ^= prow[w];
+            }
+            __syncthreads();
+        }
+        // ---- the search (:172-206)
+        const int order = min(min(order_req, kOsdMaxOrder), n - np);
+        // trial columns = the first `order` non-pivot columns; pivot columns are cleared from ev (err is overwritten there)
+        if (tid == 0) {
+            int q = 0, nt = 0;
+            uint32_t e0t = 0;
+            for (int c = 0; c < n && (nt < order || q < np); ++c) {
+                if (q < np && piv_c[q] == c) { ev[c >> 5] &= ~(1u << (c & 31)); ++q; continue; }
+                if (nt < order) {
+                    ctl[16 + 2 * NWARP + nt] = c;                                  // trial column list
+                    if ((ev[c >> 5] >> (c & 31)) & 1u) e0t |= 1u << nt;
+                    ev[c >> 5] &= ~(1u << (c & 31));
+                    ++nt;
+                }
+            }
+            ctl[0] = static_cast<int>(e0t);                // bp_err on the trial columns (what trial x = 0 uses)
+        }
+        __syncthreads();
+        const int *tcol = ctl + 16 + 2 * NWARP;
+        const uint32_t e0t = static_cast<uint32_t>(ctl[0]);
+        for (int q = tid; q < np; q += T) {
+            const uint32_t *row = Hs + piv_r[q] * NWr;
+            uint32_t par = (row[augw] & augm) ? 1u : 0u;
+            for (int w = 0; w < NWr; ++w) par ^= __popc(row[w] & ev[w] & (w == augw ? ~augm : 0xffffffffu)) & 1u;
+            uint32_t bq = 0;
+            for (int t = 0; t < order; ++t) bq |= ((row[tcol[t] >> 5] >> (tcol[t] & 31)) & 1u) << t;
+            ab[q] = par | (bq << 1);
+        }
+        int wbase = 0;
+        for (int w = lane; w < NWr; w += 32) wbase += __popc(ev[w] & (w == augw ? ~augm : 0xffffffffu));
+        wbase = __reduce_add_sync(0xffffffffu, wbase);
+        __syncthreads();
+        unsigned long long mine = ~0ull;                   // (weight << 32) | x, smallest wins = lightest, then smallest x
+        for (uint32_t x = tid; x < (1u << order); x += T) {
+            const uint32_t v = x == 0u ? e0t : x;
+            int wgt = wbase + __popc(v);
+            for (int q = 0; q < np; ++q) {
+                const uint32_t a = ab[q];
+                wgt += (a ^ __popc((a >> 1) & v)) & 1u;
+            }
+            const unsigned long long cnd = (static_cast<unsigned long long>(wgt) << 32) | x;
+            mine = cnd < mine ? cnd : mine;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long oth = __shfl_xor_sync(0xffffffffu, mine, o);
+            mine = oth < mine ? oth : mine;
+        }
+        int *red = ctl + 16 + 2 * NWARP + kOsdMaxOrder;    // per warp: weight, x
+        if (lane == 0) { red[2 * warp] = static_cast<int>(mine >> 32); red[2 * warp + 1] = static_cast<int>(mine & 0xffffffffu); }
+        __syncthreads();
+        unsigned long long bestc = ~0ull;
+        for (int w = 0; w < NWARP; ++w) {
+            const unsigned long long c2 = (static_cast<unsigned long long>(static_cast<uint32_t>(red[2 * w])) << 32) | static_cast<uint32_t>(red[2 * w + 1]);
+            bestc = c2 < bestc ? c2 : bestc;
+        }
+        const uint32_t xb = static_cast<uint32_t>(bestc);
+        const uint32_t vb = xb == 0u ? e0t : xb;
+        __syncthreads();
+        // ---- the winning error over the sorted positions, then back to the caller's column order (:60)
+        for (int t = tid; t < order; t += T)
+            if ((vb >> t) & 1u) atomicOr(&ev[tcol[t] >> 5], 1u << (tcol[t] & 31));
+        for (int q = tid; q < np; q += T) {
+            const uint32_t a = ab[q];
+            if ((a ^ __popc((a >> 1) & vb)) & 1u) atomicOr(&ev[piv_c[q] >> 5], 1u << (piv_c[q] & 31));
+        }
+        for (int w = tid; w < p.NW; w += T) erow[w] = 0u;
+        __syncthreads();
+        for (int c = tid; c < n; c += T)
+            if ((ev[c >> 5] >> (c & 31)) & 1u) {
+                const int cc = idx[c];
+                atomicOr(&erow[cc >> 5], 1u << (cc & 31));
+            }
+        if (tid == 0) {
+            atomicAdd(&p.stats[0], 1ull);
+            atomicAdd(&p.stats[1], static_cast<unsigned long long>(np));
+            atomicAdd(&p.stats[2], static_cast<unsigned long long>(1u << order));
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace bp

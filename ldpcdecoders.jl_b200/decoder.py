@@ -185,14 +185,18 @@ class BeliefPropagationDecoder:
 class BeliefPropagationOSDDecoder:
     """Mirror of BeliefPropagationOSDDecoder(H, per, max_iters; osd_order=0)
     (/root/reference/src/decoders/belief_propagation_osd.jl:17-29): fields bp_decoder, H, osd_order.
-    Only osd_order = 0 runs on the GPU (the path BASELINE config 4 names); higher orders are out of scope."""
+    osd_order = 0 (the path BASELINE config 4 names) post-processes the syndromes BP left unconverged
+    (osd(..., Val(0)), :63-125); osd_order > 0 runs the exhaustive search of osd(..., Val{O}) (:127-209) on every
+    syndrome, as the reference's decode! does."""
 
     def __init__(self, H, per, max_iters, osd_order=0, devices=None, **options):
-        if int(osd_order) != 0:
-            raise NotImplementedError("only osd_order = 0 is implemented on the GPU")
+        if not 0 <= int(osd_order) <= 12:
+            raise ValueError("osd_order must be between 0 and 12 on the GPU")
         self.bp_decoder = BeliefPropagationDecoder(H, per, max_iters, devices=devices, **options)
         self.H = H
-        self.osd_order = 0
+        self.osd_order = int(osd_order)
+        if self.osd_order:
+            self.bp_decoder.set_option("osd_order", self.osd_order)
         self.s, self.n = self.bp_decoder.s, self.bp_decoder.n
         self.last_counters = None
         self.last_osd_stats = None

@@ -135,3 +135,64 @@ def osd0_dense(H, syndrome, bp_err, ratio):
     out = np.zeros(n, dtype=np.uint8)
     out[np.asarray(order)] = corr.astype(np.uint8)
     return out
+
+
+def osdk_dense(H, syndrome, bp_err, ratio, osd_order):
+    """Dense transliteration of osd(H_sorted, syndrome, bp_err_sorted, Val{O}) for O > 0
+    (belief_propagation_osd.jl:127-209) behind the sort of :53-57 and the un-permutation of :60."""
+    H = np.asarray(H).astype(bool)
+    m, n = H.shape
+    with np.errstate(all="ignore"):
+        r = np.float64(1.0) / np.asarray(ratio, dtype=np.float64)
+        key = np.maximum(r, np.float64(1.0) - r)
+    order = sorted(range(n), key=lambda j: (-key[j], j))
+    Hs = H[:, order].copy()
+    e = np.asarray(bp_err).astype(np.int64)[order]
+    s = np.asarray(syndrome).astype(bool).copy()
+    rows, cols = [], []
+    i = j = 0
+    while i < m and j < n:
+        nz = np.nonzero(Hs[i:, j])[0]
+        if nz.size == 0:
+            j += 1
+            continue
+        k = int(nz[0])
+        if k > 0:
+            ii = i + k
+            Hs[[i, ii], :] = Hs[[ii, i], :]
+            s[i], s[ii] = s[ii], s[i]
+        for ii in range(i + 1, m):
+            if Hs[ii, j]:
+                Hs[ii, :] ^= Hs[i, :]
+                s[ii] ^= s[i]
+        rows.append(i)
+        cols.append(j)
+        i += 1
+        j += 1
+    for pi, pj in zip(rows[::-1], cols[::-1]):
+        for ii in range(pi):
+            if Hs[ii, pj]:
+                Hs[ii, :] ^= Hs[pi, :]
+                s[ii] ^= s[pi]
+    rk = len(rows)
+    osd_order = min(osd_order, n - rk)
+    err = e.astype(bool).copy()
+    best = err.copy()
+    mrc = [c for c in range(n) if c not in set(cols)]
+    min_w = n + 1
+    for x in range(1 << osd_order):
+        if x != 0:
+            for b in range(osd_order):
+                err[mrc[b]] = bool((x >> b) & 1)
+        for pi, pj in zip(rows, cols):
+            v = bool(s[pi])
+            for c in mrc:
+                v ^= bool(Hs[pi, c]) and bool(err[c])
+            err[pj] = v
+        w = int(err.sum())
+        if w < min_w:
+            min_w = w
+            best = err.copy()
+    out = np.zeros(n, dtype=np.uint8)
+    out[np.asarray(order)] = best.astype(np.uint8)
+    return out

@@ -591,6 +591,128 @@ static int osd0_one(const graph_t *g, const int64_t *colptr, const int64_t *rowv
     return (int)np;
 }
 
+/* osd(H, syndrome, bp_err, Val{O}) for O > 0: belief_propagation_osd.jl:127-209, statement by statement (physical row
+ * swaps, full Gauss-Jordan without early exit, the exhaustive 2^O search over the first O non-pivot columns with the
+ * strict `<` on the weight, so the first minimum wins).  Rows are bit-packed over the SORTED column positions.  Applied to
+ * EVERY syndrome -- decode! has no shortcut for converged ones when osd_order > 0 (:49-61).  out: n bytes in the
+ * original column order (:60).  Returns the rank r. */
+static int osdk_one(const graph_t *g, const int64_t *colptr, const int64_t *rowval, const uint8_t *syn, const uint8_t *bp_err,
+                    const double *ratio, int order, uint8_t *out, keyidx_t *ki, uint64_t *Hw, uint8_t *sv, uint8_t *err,
+                    uint8_t *best, int64_t *piv_r, int64_t *piv_c, int64_t *mrc)
+{
+    const int64_t m = g->s, n = g->n, nw = (n + 63) / 64;
+    for (int64_t j = 0; j < n; ++j) {                      /* :53-55 reliability order (same key as osd0_one) */
+        double r = 1.0 / ratio[j];
+        if (g_osd_key_mode == 1) r = exp(log(r));
+        double q = 1.0 - r;
+        ki[j].key = (r > q) ? r : q;
+        ki[j].idx = j;
+    }
+    qsort(ki, (size_t)n, sizeof(keyidx_t), cmp_keyidx_desc);
+    memset(Hw, 0, sizeof(uint64_t) * (size_t)(m * nw));
+    for (int64_t j = 0; j < n; ++j) {                      /* :56-57 */
+        int64_t c = ki[j].idx;
+        err[j] = bp_err[c];
+        for (int64_t e = colptr[c]; e < colptr[c + 1]; ++e) Hw[rowval[e] * nw + (j >> 6)] |= 1ull << (j & 63);
+    }
+    for (int64_t i = 0; i < m; ++i) sv[i] = syn[i] & 1;    /* :137 s = copy(syndrome) */
+    int64_t np = 0, i = 0, j = 0;
+    while (i < m && j < n) {                               /* :139-160 */
+        int64_t k = -1;
+        for (int64_t ii = i; ii < m; ++ii) if (OSD_BIT(Hw + ii * nw, j)) { k = ii; break; }
+        if (k < 0) { ++j; continue; }
+        if (k != i) {
+            for (int64_t w = 0; w < nw; ++w) { uint64_t t = Hw[i * nw + w]; Hw[i * nw + w] = Hw[k * nw + w]; Hw[k * nw + w] = t; }
+            uint8_t t = sv[i]; sv[i] = sv[k]; sv[k] = t;
+        }
+        for (int64_t ii = i + 1; ii < m; ++ii)
+            if (OSD_BIT(Hw + ii * nw, j)) {
+                for (int64_t w = 0; w < nw; ++w) Hw[ii * nw + w] ^= Hw[i * nw + w];
+                sv[ii] ^= sv[i];
+            }
+        piv_r[np] = i; piv_c[np] = j; ++np;
+        ++i; ++j;
+    }
+    for (int64_t q = np - 1; q >= 0; --q) {                /* :163-170 diagonalise */
+        const int64_t pi = piv_r[q], pj = piv_c[q];
+        for (int64_t ii = 0; ii < pi; ++ii)
+            if (OSD_BIT(Hw + ii * nw, pj)) {
+                for (int64_t w = 0; w < nw; ++w) Hw[ii * nw + w] ^= Hw[pi * nw + w];
+                sv[ii] ^= sv[pi];
+            }
+    }
+    if (order > n - np) order = (int)(n - np);            /* :172-175 */
+    int64_t nm = 0;                                        /* most_reliable_cols = setdiff(1:n, pivot columns), ascending */
+    {
+        int64_t q = 0;
+        for (int64_t c = 0; c < n; ++c) {
+            if (q < np && piv_c[q] == c) { ++q; continue; }
+            mrc[nm++] = c;
+        }
+    }
+    memcpy(best, err, (size_t)n);                          /* best_err = copy(bp_err) */
+    int64_t min_weight = n + 1;
+    for (uint64_t x = 0; x < (1ull << order); ++x) {       /* :182-206 */
+        if (x != 0)
+            for (int b = 0; b < order; ++b) err[mrc[b]] = (uint8_t)((x >> b) & 1);
+        for (int64_t q = 0; q < np; ++q) {
+            const int64_t pi = piv_r[q], pj = piv_c[q];
+            uint8_t v = sv[pi];
+            for (int64_t t = 0; t < nm; ++t) v ^= (uint8_t)(OSD_BIT(Hw + pi * nw, mrc[t]) & err[mrc[t]]);
+            err[pj] = v;
+        }
+        int64_t weight = 0;
+        for (int64_t c = 0; c < n; ++c) weight += err[c];
+        if (weight < min_weight) { min_weight = weight; memcpy(best, err, (size_t)n); }
+    }
+    for (int64_t c = 0; c < n; ++c) out[ki[c].idx] = best[c];   /* :60 err[invperm(...)] */
+    return (int)np;
+}
+
+/* BP followed by OSD of order `order` > 0 on every column (decode!(::BeliefPropagationOSDDecoder, ...) with osd_order = order). */
+int bp_oracle_bposd_order_batch(int64_t s, int64_t n, const int64_t *colptr, const int64_t *rowval, double per, int32_t max_iters,
+                                int32_t order, int64_t B, const uint8_t *syn, uint8_t *err, uint8_t *conv, int32_t nthreads)
+{
+    graph_t g;
+    int rc = build_graph(&g, s, n, colptr, rowval);
+    if (rc) return rc;
+    if (nthreads < 1) nthreads = 1;
+    int fail = 0;
+    const size_t nn = (size_t)(n ? n : 1), ss = (size_t)(s ? s : 1), nw = (size_t)((n + 63) / 64 + 1);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        size_t msz = g.E ? (size_t)g.E : 1;
+        double *a = (double *)malloc(sizeof(double) * msz), *b = (double *)malloc(sizeof(double) * msz);
+        double *ratio = (double *)malloc(sizeof(double) * nn);
+        uint8_t *bp = (uint8_t *)malloc(nn), *sv = (uint8_t *)malloc(ss), *e1 = (uint8_t *)malloc(nn), *best = (uint8_t *)malloc(nn);
+        keyidx_t *ki = (keyidx_t *)malloc(sizeof(keyidx_t) * nn);
+        uint64_t *Hw = (uint64_t *)malloc(sizeof(uint64_t) * ss * nw);
+        int64_t *pr = (int64_t *)malloc(sizeof(int64_t) * ss), *pc = (int64_t *)malloc(sizeof(int64_t) * ss);
+        int64_t *mrc = (int64_t *)malloc(sizeof(int64_t) * nn);
+        if (!a || !b || !ratio || !bp || !sv || !e1 || !best || !ki || !Hw || !pr || !pc || !mrc) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            fail = 1;
+        } else {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+            for (int64_t c = 0; c < B; ++c) {
+                const uint8_t *sc = syn + (size_t)c * (size_t)s;
+                int32_t itc = 0;
+                conv[c] = (uint8_t)decode_edge(&g, per, max_iters, sc, a, b, bp, ratio, &itc);
+                osdk_one(&g, colptr, rowval, sc, bp, ratio, order, err + (size_t)c * (size_t)n, ki, Hw, sv, e1, best, pr, pc, mrc);
+            }
+        }
+        free(a); free(b); free(ratio); free(bp); free(sv); free(e1); free(best); free(ki); free(Hw); free(pr); free(pc); free(mrc);
+    }
+    free_graph(&g);
+    return fail ? -1 : 0;
+}
+
 /* BP followed by OSD-0 on every column of the batch (decode! of the BP+OSD decoder applied per
  * column).  err: n x B bytes out (the OSD result), conv: BP's converged flag (:60), bp_err:
  * optional n x B bytes (BP's own decisions), pivots: optional B int32 (pivots used). */

@@ -49,6 +49,9 @@ def load():
     lib.bp_oracle_bposd_batch.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double,
                                           ctypes.c_int32, ctypes.c_int64, u8p, u8p, u8p, u8p,
                                           ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
+    lib.bp_oracle_bposd_order_batch.restype = ctypes.c_int
+    lib.bp_oracle_bposd_order_batch.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_int64, u8p, u8p, u8p, ctypes.c_int32]
     lib.bp_oracle_set_minsum_scale.argtypes = [ctypes.c_double]
     lib.bp_oracle_set_minsum_scale.restype = None
     lib.bp_oracle_set_osd_key_mode.argtypes = [ctypes.c_int]
@@ -131,6 +134,26 @@ def bposd_decode(H, per, max_iters, syndromes, nthreads=1, key_mode=0):
     if rc != 0:
         raise RuntimeError("bp_oracle_bposd_batch failed: %d" % rc)
     return dict(errors=err, converged=conv.astype(bool), bp_errors=bp, pivots=piv)
+
+
+def bposd_order_decode(H, per, max_iters, osd_order, syndromes, nthreads=1, key_mode=0):
+    """Restated decode!(::BeliefPropagationOSDDecoder, syndrome) with osd_order > 0 (belief_propagation_osd.jl:49-61,
+    osd(..., Val{O}) :127-209) applied to every column.  Returns dict(errors (n,B) uint8, converged (B,) bool -- BP's flag)."""
+    lib = load()
+    lib.bp_oracle_set_osd_key_mode(int(key_mode))
+    s, n, colptr, rowval = csc_arrays(H)
+    syn = np.asfortranarray(np.asarray(syndromes).astype(np.uint8))
+    if syn.ndim == 1:
+        syn = np.asfortranarray(syn.reshape(s, 1))
+    B = syn.shape[1]
+    err = np.zeros((n, B), dtype=np.uint8, order="F")
+    conv = np.zeros(B, dtype=np.uint8)
+    rc = lib.bp_oracle_bposd_order_batch(s, n, _p(colptr, ctypes.c_int64), _p(rowval, ctypes.c_int64), float(per), int(max_iters),
+                                         int(osd_order), B, _p(syn, ctypes.c_uint8), _p(err, ctypes.c_uint8), _p(conv, ctypes.c_uint8),
+                                         int(nthreads))
+    if rc != 0:
+        raise RuntimeError("bp_oracle_bposd_order_batch failed: %d" % rc)
+    return dict(errors=err, converged=conv.astype(bool))
 
 
 def sample(H, per, seed, first, B):

@@ -46,3 +46,17 @@ def test_css_logicals_of_surface_and_gross_codes(codes):
         assert ((L @ Hz.T).toarray() % 2 == 0).all()
         Lz = codes.css_logicals(Hz, Hx)
         assert np.linalg.matrix_rank((L @ Lz.T).toarray() % 2) >= 1
+
+
+def test_pcm_text_io_round_trip(codes, tmp_path):
+    """save_pcm / load_pcm (parity_generator.jl:47-54): tab-separated 0/1 rows as Julia's writedlm writes them."""
+    import numpy as np
+    H = codes.parity_check_matrix(60, 6, 3, seed=5)
+    assert (np.asarray(H.sum(axis=1)).ravel() == 6).all() and (np.asarray(H.sum(axis=0)).ravel() == 3).all()
+    path = tmp_path / "H.txt"
+    codes.save_pcm(H, path)
+    first = open(path).readline().rstrip("\n").split("\t")
+    assert len(first) == 60 and set(first) <= {"0", "1"}
+    assert (codes.load_pcm(path) != H).nnz == 0
+    (tmp_path / "J.txt").write_text("1.0 0.0 1.0\n0 1 1\n")           # readdlm-style floats
+    assert codes.load_pcm(tmp_path / "J.txt").toarray().tolist() == [[1, 0, 1], [0, 1, 1]]

@@ -872,3 +872,38 @@ def test_golden_osd_fixtures_on_gpu(pkg, name):
     g = run_gpu_bposd(pkg, H, float(z["per"]), int(zo["max_iters"]), z["syndromes"])
     assert np.array_equal(g["errors"], zo["errors"]) and np.array_equal(g["converged"], zo["converged"])
     assert g["stats"][0] == int((~zo["converged"]).sum()) and g["stats"][1] == int(zo["pivots"][~zo["converged"]].sum())
+
+
+@pytest.mark.parametrize("name,per,mi,B", [("C3", 0.08, 6, 600), ("C2", 0.05, 8, 400), ("C1", 0.05, 3, 24), ("C4", 0.04, 4, 40)])
+def test_higher_order_osd_matches_restated_reference(pkg, oracle, codes, name, per, mi, B):
+    """BeliefPropagationOSDDecoder(H, per, max_iters; osd_order = O > 0): osd(..., Val{O}) (belief_propagation_osd.jl:127-209)
+    on every column -- bit for bit against the restated reference (physical row swaps, strict `<` in ascending trial order)."""
+    H, _, _ = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 909, 0, B)
+    for order in ((1, 3, 5) if name != "C4" else (2,)):
+        ref = oracle.bposd_order_decode(H, per, mi, order, syn, nthreads=oracle.num_threads())
+        g = run_gpu_bposd(pkg, H, per, mi, syn, osd_order=order)
+        bad = np.nonzero((g["errors"] != ref["errors"]).any(axis=0) | (g["converged"] != ref["converged"]))[0]
+        assert bad.size == 0, (name, order, bad[:10])
+        assert ((H @ g["errors"]) % 2 == syn).all()
+        assert g["stats"][0] == B            # every column goes through the search
+
+
+def test_higher_order_osd_edge_cases(pkg, oracle, codes):
+    """Order larger than the information set (clamped, :172-175), rank-deficient H with syndromes outside the column space
+    (the outcome then depends on the reference's row order), max_iters = 0, single-syndrome decode!."""
+    H = sp.csc_matrix(np.array([[1, 1, 0, 0], [0, 1, 1, 0], [1, 0, 1, 0]], dtype=np.uint8))
+    syn = np.array([[1, 0, 1], [1, 1, 1], [0, 0, 1], [0, 0, 0], [1, 1, 0]], dtype=np.uint8).T
+    for mi in (0, 3):
+        for order in (1, 7):
+            ref = oracle.bposd_order_decode(H, 0.1, mi, order, syn)
+            g = run_gpu_bposd(pkg, H, 0.1, mi, syn, osd_order=order)
+            assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["converged"], ref["converged"]), (mi, order)
+    Hg = codes.gross_x()
+    _, s2 = oracle.sample(Hg, 0.1, 4, 0, 20)
+    ref = oracle.bposd_order_decode(Hg, 0.1, 4, 4, s2)
+    dec = pkg.BeliefPropagationOSDDecoder(Hg, 0.1, 4, osd_order=4)
+    for c in range(5):
+        guess, conv = pkg.decode_b(dec, s2[:, c])
+        assert np.array_equal(guess.astype(np.uint8), ref["errors"][:, c]) and conv == bool(ref["converged"][c])
+    dec.close()

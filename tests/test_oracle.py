@@ -245,3 +245,34 @@ def test_golden_osd_fixtures_and_julia_twins(oracle, name):
     assert np.array_equal(ld(".iters.txt").ravel(), z["iters"])
     assert np.array_equal(ld(".osd_errors.txt"), zo["errors"]) and np.array_equal(ld(".osd_converged.txt").ravel(), zo["converged"].astype(int))
     assert int(ld(".osd_meta.txt").ravel()[0]) == int(zo["max_iters"])
+
+
+def test_higher_order_osd_restatement(oracle, codes):
+    """osd(..., Val{O}), O > 0 (belief_propagation_osd.jl:127-209): the C restatement equals the independent dense
+    transliteration; every output reproduces its syndrome; the weight never exceeds that of the order-0 member of the
+    search (x = 0) and does not grow with the order."""
+    from oracle import bp_dense
+    rng = np.random.default_rng(3)
+    cases = [(codes.gross_x(), 0.08, 6), (codes.surface_x(5), 0.08, 4), (codes.gallager(24, 4, 3, seed=2), 0.1, 3)]
+    for H, per, mi in cases:
+        _, syn = oracle.sample(H, per, 31, 0, 40)
+        bp = oracle.batch_decode(H, per, mi, syn, want_ratio=True)
+        prev_w = None
+        for order in (1, 2, 5):
+            r = oracle.bposd_order_decode(H, per, mi, order, syn, nthreads=2)
+            assert np.array_equal(r["converged"], bp["converged"])
+            for c in range(syn.shape[1]):
+                want = bp_dense.osdk_dense(H.toarray(), syn[:, c], bp["errors"][:, c], bp["ratio"][:, c], order)
+                assert np.array_equal(r["errors"][:, c], want), (order, c)
+            assert ((H @ r["errors"]) % 2 == syn).all()
+            w = r["errors"].sum(axis=0)
+            if prev_w is not None:
+                assert (w <= prev_w).all()
+            prev_w = w
+    # rank-deficient H with syndromes outside the column space, order larger than the information set
+    H = sp.csc_matrix(np.array([[1, 1, 0, 0], [0, 1, 1, 0], [1, 0, 1, 0]], dtype=np.uint8))
+    syn = np.array([[1, 0, 1], [1, 1, 1], [0, 0, 1]], dtype=np.uint8).T
+    bp = oracle.batch_decode(H, 0.1, 3, syn, want_ratio=True)
+    r = oracle.bposd_order_decode(H, 0.1, 3, 7, syn)
+    for c in range(syn.shape[1]):
+        assert np.array_equal(r["errors"][:, c], bp_dense.osdk_dense(H.toarray(), syn[:, c], bp["errors"][:, c], bp["ratio"][:, c], 7))
