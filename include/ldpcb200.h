@@ -164,6 +164,18 @@ int ldpcb200_bposd_decode_batch(ldpcb200_t *h, int64_t B,
                                 void *errors, int32_t err_fmt, int64_t err_ld,
                                 uint8_t *converged, int32_t *iters, int64_t *counters, int64_t *osd_stats);
 
+/* Replaces decode!(::BPOTSDecoder, syndrome) (src/decoders/bpots_decoder.jl:226-340; constructor BPOTSDecoder(H, per, max_iters;
+ * T = 9, C = 2.0) :90-111) applied to every column of a batch, which is what the generic batchdecode! (abstract_decoder.jl:31-42)
+ * does with it.  The handle supplies H, per and max_iters (its variant is irrelevant: BP-OTS has its own Float64 LLR-domain
+ * tanh/atanh updates, depolarising prior log((1 - 2 per/3)/(2 per/3)), oscillation counting, best-so-far tracking and bias -C every
+ * T iterations).  errors receives best_decisions, converged the flag decode! returns, iters (nullable) the executed iterations.
+ * One CTA per syndrome; both message arrays of a syndrome must fit in shared memory (LDPCB200_EUNSUPPORTED otherwise).
+ * tanh / atanh / log are CUDA's where the reference uses Julia's: outcomes agree except where a last-bit difference gets amplified. */
+int ldpcb200_bpots_decode_batch(ldpcb200_t *h, int64_t B,
+                                const void *syndromes, int32_t syn_fmt, int64_t syn_ld,
+                                void *errors, int32_t err_fmt, int64_t err_ld,
+                                uint8_t *converged, int32_t *iters, int32_t T, double C);
+
 /* The OSD-0 stage alone on device-resident buffers (native packed rows), after ldpcb200_decode_device with a
  * posterior-ratio output: d_err_words holds BP's decisions on entry and the OSD result on return;
  * d_posterior_ratio is [B][n].  d_stats: nullable device pointer to LDPCB200_NUM_OSD_STATS uint64 the kernel

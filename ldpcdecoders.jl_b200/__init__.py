@@ -5,9 +5,9 @@ csrc/ holds the CUDA kernels and the C ABI (include/ldpcb200.h); decoder.py mirr
 reference's decoder interface on top of that ABI; codes.py builds the benchmark matrices.
 """
 from . import _lib, codes, sharding                                              # noqa: F401
-from .decoder import (BeliefPropagationDecoder, BeliefPropagationOSDDecoder,     # noqa: F401
+from .decoder import (BeliefPropagationDecoder, BeliefPropagationOSDDecoder, BPOTSDecoder,     # noqa: F401
                       BeliefPropagationScratchSpace,
                       decode_b, batchdecode_b, reset_b, ler_curve)
 
-__all__ = ["BeliefPropagationDecoder", "BeliefPropagationOSDDecoder", "BeliefPropagationScratchSpace", "decode_b", "batchdecode_b",
+__all__ = ["BeliefPropagationDecoder", "BeliefPropagationOSDDecoder", "BPOTSDecoder", "BeliefPropagationScratchSpace", "decode_b", "batchdecode_b",
            "reset_b", "ler_curve", "codes"]

@@ -24,7 +24,7 @@ SYMBOLS = [
     "ldpcb200_decode_device", "ldpcb200_sample_device", "ldpcb200_score_device",
     "ldpcb200_launch_count", "ldpcb200_selftest_division",
     "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device", "ldpcb200_kernel_profile",
-    "ldpcb200_set_logicals", "ldpcb200_score_logical_device", "ldpcb200_set_per", "ldpcb200_sample_decode_score",
+    "ldpcb200_set_logicals", "ldpcb200_score_logical_device", "ldpcb200_set_per", "ldpcb200_sample_decode_score", "ldpcb200_bpots_decode_batch",
 ]
 NUM_HARNESS_COUNTERS = 8
 HARNESS_FIELDS = ("shots", "converged", "iterations", "exact_matches", "syndrome_satisfied", "failures", "residual_weight", "osd_processed")
@@ -75,6 +75,7 @@ def load():
     lib.ldpcb200_osd0_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.ldpcb200_sample_device.argtypes = [vp, i32, i64, i64, u64, dbl, vp, vp, vp]
     lib.ldpcb200_score_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.ldpcb200_bpots_decode_batch.argtypes = [vp, i64, vp, i32, i64, vp, i32, i64, vp, vp, i32, dbl]
     lib.ldpcb200_set_logicals.argtypes = [vp, i64, vp, vp, i32]
     lib.ldpcb200_score_logical_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
     lib.ldpcb200_set_per.argtypes = [vp, dbl]

@@ -17,7 +17,7 @@ SOURCES = (["ldpcb200.cu"] + ["bp_inst_m%d_b%d.cu" % (m, b) for m in (0, 1, 2) f
               "bp_inst_single_fast.cu", "bp_inst_smem_fast.cu"])
 KERNEL_HEADERS = ["bp_math.cuh", "bp_kernel.cuh", "bp_smem.cuh", "bp_smem_inst.cuh", "bp_launch.h", "bp_launch_inst.cuh",
                   "../../include/ldpcb200.h"]
-HEADERS = KERNEL_HEADERS + ["formats.cuh", "osd.cuh", "bp_single.h", "bp_single.cuh"]
+HEADERS = KERNEL_HEADERS + ["formats.cuh", "osd.cuh", "bpots.cuh", "bp_single.h", "bp_single.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -26,6 +26,7 @@
 #include "bp_single.h"
 #include "formats.cuh"
 #include "osd.cuh"
+#include "bpots.cuh"
 
 namespace {
 
@@ -988,6 +989,47 @@ int osdk_on_device(ldpcb200 *h, DeviceCtx &d, DeviceCtx::StageSet &S, int64_t B,
     return 0;
 }
 
+// ---- BP-OTS (bpots.cuh): one CTA per syndrome.  Stream-ordered.
+struct BpotsArgs { int T; double C; };
+
+int bpots_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words, uint8_t *conv, int32_t *iters,
+                    const BpotsArgs &a, cudaStream_t st)
+{
+    if (B <= 0) return 0;
+    CU(cudaSetDevice(d.device));
+    if (a.T < 1) return fail(LDPCB200_EINVAL, "BP-OTS: the biasing period T must be at least 1");
+    bp::BpotsParams p{};
+    p.s = static_cast<int>(h->s); p.n = static_cast<int>(h->n); p.E = static_cast<int>(h->E);
+    p.SW = h->SW; p.NW = h->NW; p.max_iters = h->max_iters; p.T = a.T; p.C = a.C; p.B = B;
+    {   // log.((1 .- (2*per/3)) ./ (2*per/3))  (bpots_decoder.jl:231), IEEE double on the host
+        volatile double q = 2 * h->per / 3;
+        volatile double r = (1 - q) / q;
+        p.prior = std::log(r);
+    }
+    long long off = static_cast<long long>(std::max<int64_t>(h->E, 1)) * 8;
+    p.off_cv = static_cast<int>(off);     off *= 2;
+    p.off_omega = static_cast<int>(off);  off += static_cast<long long>(std::max<int64_t>(h->n, 1)) * 8;
+    p.off_llr = static_cast<int>(off);    off += static_cast<long long>(std::max<int64_t>(h->n, 1)) * 8;
+    p.off_osc = static_cast<int>(off);    off += static_cast<long long>(std::max<int64_t>(h->n, 1)) * 4;
+    p.off_par = static_cast<int>(off);    off += static_cast<long long>(std::max<int64_t>(h->s, 1)) * 4;
+    p.off_dec = static_cast<int>(off);    off += 3 * std::max<int64_t>(h->n, 1);
+    off = (off + 15) / 16 * 16;
+    p.off_red = static_cast<int>(off);    off += 512;
+    if (off > d.smem_optin)
+        return fail(LDPCB200_EUNSUPPORTED, "BP-OTS: the two message arrays of one syndrome (%lld bytes with state) do not fit in shared memory",
+                    off);
+    const int smem = static_cast<int>(off);
+    p.rowptr = d.d_rowptr; p.colptr = d.d_colptr; p.ve_slot = d.d_ve_slot; p.ve_chk = d.d_ve_chk;
+    p.syn_words = syn_words; p.err_words = err_words; p.conv = conv; p.iters = iters;
+    const int per_sm = std::max(1, std::min(8, d.smem_per_sm / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(d.sm_count) * per_sm));
+    CU(cudaFuncSetAttribute(bp::bpots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    bp::bpots_kernel<<<grid, bp::kBpotsThreads, smem, st>>>(p);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 size_t fmt_bytes(int fmt, int64_t rows, int64_t ld, int64_t B, int RW)
 {
     switch (fmt) {
@@ -1115,13 +1157,14 @@ bool is_pageable(const void *p)
 // One device's share [b0, b0+Bd) of a host batch, processed in chunks.
 int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t Btot, const void *syndromes,
                       int syn_fmt, int64_t syn_ld, void *errors, int err_fmt, int64_t err_ld, uint8_t *converged,
-                      int32_t *iters, double *ratio, int64_t *counters_out, bool osd = false, int64_t *osd_stats_out = nullptr)
+                      int32_t *iters, double *ratio, int64_t *counters_out, bool osd = false, int64_t *osd_stats_out = nullptr,
+                      const BpotsArgs *ots = nullptr)
 {
     CU(cudaSetDevice(d.device));
     const int64_t s = h->s, n = h->n;
     {
         const int64_t limit = h->opt_small_batch < 0 ? d.sm_count : h->opt_small_batch;
-        if (!osd && b0 == 0 && Bd == Btot && Bd <= limit && h->opt_chunk <= 0 &&
+        if (!osd && !ots && b0 == 0 && Bd == Btot && Bd <= limit && h->opt_chunk <= 0 &&
             static_cast<double>(Bd) * (static_cast<double>(n) * 8.0 * (ratio ? 2 : 1) + static_cast<double>(s) * 8.0) < 64.0 * 1048576.0)
             return decode_host_tiny(h, d, Bd, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, ratio, counters_out);
     }
@@ -1235,6 +1278,9 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         if (have_prev_decode) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
         // (OSD-0 only reads the ratios of unconverged syndromes: those of iteration max_iters; a higher order post-processes
         //  every syndrome, so the ratios of each syndrome's own last iteration are needed)
+        if (ots)
+            rc = bpots_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(), *ots, st);
+        else
         rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
                               (ratio || (osd && h->max_iters > 0)) ? S.ratio.as<double>() : nullptr,
                               d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0);
@@ -1600,7 +1646,7 @@ int ldpcb200_decode_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uin
 
 static int decode_batch_impl(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
                              int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, double *posterior_ratio,
-                             int64_t *counters, bool osd, int64_t *osd_stats)
+                             int64_t *counters, bool osd, int64_t *osd_stats, const BpotsArgs *ots = nullptr)
 {
     if (!h) return fail(LDPCB200_EINVAL, "null handle");
     if (osd_stats) memset(osd_stats, 0, sizeof(int64_t) * LDPCB200_NUM_OSD_STATS);
@@ -1630,7 +1676,7 @@ static int decode_batch_impl(ldpcb200_t *h, int64_t B, const void *syndromes, in
         if (lo[k + 1] > lo[k])
             rcs[k] = decode_host_range(h, h->dev[k], lo[k], lo[k + 1] - lo[k], B, syndromes, syn_fmt, syn_ld, errors, err_fmt,
                                        err_ld, converged, iters, posterior_ratio, &ctr[static_cast<size_t>(k) * LDPCB200_NUM_COUNTERS],
-                                       osd, &ost[static_cast<size_t>(k) * LDPCB200_NUM_OSD_STATS]);
+                                       osd, &ost[static_cast<size_t>(k) * LDPCB200_NUM_OSD_STATS], ots);
         if (rcs[k]) errs[k] = g_err;
     };
     if (nd == 1) {
@@ -1680,6 +1726,13 @@ int ldpcb200_bposd_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes,
 {
     return decode_batch_impl(h, B, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, nullptr, counters,
                              true, osd_stats);
+}
+
+int ldpcb200_bpots_decode_batch(ldpcb200_t *h, int64_t B, const void *syndromes, int32_t syn_fmt, int64_t syn_ld, void *errors,
+                                int32_t err_fmt, int64_t err_ld, uint8_t *converged, int32_t *iters, int32_t T, double C)
+{
+    const BpotsArgs a{T, C};
+    return decode_batch_impl(h, B, syndromes, syn_fmt, syn_ld, errors, err_fmt, err_ld, converged, iters, nullptr, nullptr, false, nullptr, &a);
 }
 
 int ldpcb200_osd0_device(ldpcb200_t *h, int32_t dev_slot, int64_t B, const uint32_t *d_syn_words, uint32_t *d_err_words,

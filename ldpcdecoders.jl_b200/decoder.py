@@ -205,11 +205,36 @@ class BeliefPropagationOSDDecoder:
         self.bp_decoder.close()
 
 
+class BPOTSDecoder:
+    """Mirror of BPOTSDecoder(H, per, max_iters; T=9, C=2.0) (/root/reference/src/decoders/bpots_decoder.jl:42-111):
+    fields per, max_iters, s, n, T, C, sparse_H, sparse_HT; decode_b / batchdecode_b return (best_decisions, converged)."""
+
+    def __init__(self, H, per, max_iters, T=9, C=2.0, devices=None, **options):
+        self._bp = BeliefPropagationDecoder(H, per, max_iters, devices=devices, **options)     # graph tables + handle
+        self.per, self.max_iters, self.s, self.n = self._bp.per, self._bp.max_iters, self._bp.s, self._bp.n
+        self.sparse_H, self.sparse_HT = self._bp.sparse_H, self._bp.sparse_HT
+        self.T, self.C = int(T), float(C)
+        self.last_counters = None
+
+    def decode_raw(self, B, syn, syn_fmt, syn_ld, err, err_fmt, err_ld, conv, iters=None):
+        _lib.check(self._bp._lib.ldpcb200_bpots_decode_batch(
+            self._bp._h, int(B), syn.ctypes.data, syn_fmt, int(syn_ld), err.ctypes.data, err_fmt, int(err_ld), conv.ctypes.data,
+            iters.ctypes.data if iters is not None else None, self.T, self.C))
+
+    def info(self):
+        return self._bp.info()
+
+    def close(self):
+        self._bp.close()
+
+
 def reset_b(decoder):
     """LDPCDecoders.reset!(decoder): the GPU path keeps no host scratch between calls."""
     if isinstance(decoder, BeliefPropagationOSDDecoder):
         reset_b(decoder.bp_decoder)
         return decoder
+    if isinstance(decoder, BPOTSDecoder):
+        return decoder                          # bpots_decoder.jl:144-156: all state is re-initialised inside the kernel
     decoder.scratch.log_probabs[:] = 0.0
     decoder.scratch.err[:] = 0.0
     return decoder
@@ -251,7 +276,11 @@ def batchdecode_b(decoder, syndromes, errors, success=None, iters=None, posterio
         assert ratio.shape == (decoder.n, B) and ratio.dtype == np.float64 and ratio.flags.f_contiguous
     if iters is not None:
         assert iters.shape == (B,) and iters.dtype == np.int32
-    if isinstance(decoder, BeliefPropagationOSDDecoder):
+    if isinstance(decoder, BPOTSDecoder):
+        if ratio is not None:
+            raise ValueError("posterior_ratio is not an output of the BP-OTS decoder")
+        decoder.decode_raw(B, syn_f, syn_fmt, max(decoder.s, 1), err_f, err_fmt, max(decoder.n, 1), success.view(np.uint8), iters)
+    elif isinstance(decoder, BeliefPropagationOSDDecoder):
         # generic batchdecode! (abstract_decoder.jl:31-42) over decode!(::BeliefPropagationOSDDecoder)
         if ratio is not None:
             raise ValueError("posterior_ratio is not an output of the BP+OSD decoder")
@@ -274,6 +303,12 @@ def decode_b(decoder, syndrome):
     if syn.dtype not in (np.bool_, np.uint8, np.int8, np.int64):
         syn = syn.astype(np.int64)
     syn_f = np.asfortranarray(syn.reshape(decoder.s, 1))
+    if isinstance(decoder, BPOTSDecoder):
+        # decode!(::BPOTSDecoder) returns best_decisions (a Vector{Int}) and the converged flag (bpots_decoder.jl:291,339)
+        out = np.zeros((decoder.n, 1), dtype=np.int64, order="F")
+        conv = np.zeros(1, dtype=np.uint8)
+        decoder.decode_raw(1, syn_f, _fmt_of(syn_f, "syndrome"), max(decoder.s, 1), out, _lib.FMT_I64, max(decoder.n, 1), conv)
+        return out[:, 0], bool(conv[0])
     if isinstance(decoder, BeliefPropagationOSDDecoder):
         # decode!(::BeliefPropagationOSDDecoder) returns a fresh Bool vector and BP's flag (:60)
         out = np.zeros((decoder.n, 1), dtype=np.bool_, order="F")

@@ -10,6 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "bp_oracle.c")
+_SRC_OTS = os.path.join(_HERE, "bpots_oracle.c")
 _OUT_DIR = os.path.join(_HERE, "_build")
 _SO = os.path.join(_OUT_DIR, "libbporacle.so")
 _lib = None
@@ -20,11 +21,11 @@ CFLAGS = ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "
 
 def build(force=False):
     """Compile the C restatement with gcc (build() of __graft_entry__ calls this)."""
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(_SRC):
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(_SRC), os.path.getmtime(_SRC_OTS)):
         return _SO
     os.makedirs(_OUT_DIR, exist_ok=True)
     tmp = _SO + ".tmp.%d" % os.getpid()
-    subprocess.check_call(["gcc"] + CFLAGS + [_SRC, "-o", tmp, "-lm"])
+    subprocess.check_call(["gcc"] + CFLAGS + [_SRC, _SRC_OTS, "-o", tmp, "-lm"])
     os.replace(tmp, _SO)
     return _SO
 
@@ -52,6 +53,9 @@ def load():
     lib.bp_oracle_bposd_order_batch.restype = ctypes.c_int
     lib.bp_oracle_bposd_order_batch.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
                                                 ctypes.c_int64, u8p, u8p, u8p, ctypes.c_int32]
+    lib.bpots_oracle_batch.restype = ctypes.c_int
+    lib.bpots_oracle_batch.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, ctypes.c_double, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_double, ctypes.c_int64, u8p, u8p, u8p, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
     lib.bp_oracle_set_minsum_scale.argtypes = [ctypes.c_double]
     lib.bp_oracle_set_minsum_scale.restype = None
     lib.bp_oracle_set_osd_key_mode.argtypes = [ctypes.c_int]
@@ -154,6 +158,26 @@ def bposd_order_decode(H, per, max_iters, osd_order, syndromes, nthreads=1, key_
     if rc != 0:
         raise RuntimeError("bp_oracle_bposd_order_batch failed: %d" % rc)
     return dict(errors=err, converged=conv.astype(bool))
+
+
+def bpots_decode(H, per, max_iters, syndromes, T=9, C=2.0, nthreads=1):
+    """Restated decode!(::BPOTSDecoder, syndrome) (bpots_decoder.jl:226-340) applied to every column.
+    Returns dict(errors (n,B) uint8 -- best_decisions, converged (B,) bool, iters (B,) int32)."""
+    lib = load()
+    s, n, colptr, rowval = csc_arrays(H)
+    syn = np.asfortranarray(np.asarray(syndromes).astype(np.uint8))
+    if syn.ndim == 1:
+        syn = np.asfortranarray(syn.reshape(s, 1))
+    B = syn.shape[1]
+    err = np.zeros((n, B), dtype=np.uint8, order="F")
+    conv = np.zeros(B, dtype=np.uint8)
+    iters = np.zeros(B, dtype=np.int32)
+    rc = lib.bpots_oracle_batch(s, n, _p(colptr, ctypes.c_int64), _p(rowval, ctypes.c_int64), float(per), int(max_iters), int(T), float(C),
+                                B, _p(syn, ctypes.c_uint8), _p(err, ctypes.c_uint8), _p(conv, ctypes.c_uint8), _p(iters, ctypes.c_int32),
+                                int(nthreads))
+    if rc != 0:
+        raise RuntimeError("bpots_oracle_batch failed: %d" % rc)
+    return dict(errors=err, converged=conv.astype(bool), iters=iters)
 
 
 def sample(H, per, seed, first, B):

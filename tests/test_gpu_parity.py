@@ -907,3 +907,67 @@ def test_higher_order_osd_edge_cases(pkg, oracle, codes):
         guess, conv = pkg.decode_b(dec, s2[:, c])
         assert np.array_equal(guess.astype(np.uint8), ref["errors"][:, c]) and conv == bool(ref["converged"][c])
     dec.close()
+
+
+def _cycle_matrix(n):
+    """create_cycle_matrix of /root/reference/test/test_bpots.jl:14-25."""
+    r, c = [], []
+    for j in range(n):
+        r += [j, j]
+        c += [(j + 1) % n, j]
+    return sp.csc_matrix((np.ones(2 * n, dtype=np.uint8), (r, c)), shape=(n, n))
+
+
+def _run_bpots(pkg, H, per, mi, syn, T=9, C=2.0, fmt=np.uint8, **opts):
+    dec = pkg.BPOTSDecoder(H, per, mi, T=T, C=C, **opts)
+    n, B = H.shape[1], syn.shape[1]
+    errors = np.full((n, B), 1, dtype=fmt, order="F")
+    iters = np.zeros(B, dtype=np.int32)
+    _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn.astype(fmt)), errors, iters=iters)
+    dec.close()
+    return dict(errors=errors.astype(np.uint8), converged=success.copy(), iters=iters)
+
+
+@pytest.mark.parametrize("name,per,mi,T,C,B", [("C3", 0.05, 50, 9, 2.0, 3000), ("C3", 0.1, 40, 5, 3.0, 1500), ("C2", 0.05, 60, 9, 2.0, 1500),
+                                               ("C1", 0.03, 30, 9, 2.0, 100), ("C4", 0.03, 30, 7, 5.0, 150)])
+def test_bpots_matches_restated_reference(pkg, oracle, codes, name, per, mi, T, C, B):
+    """BP-OTS (bpots_decoder.jl:226-340) on the GPU against the C restatement.  tanh / atanh / log come from two different
+    math libraries (CUDA's and glibc's; the reference has Julia's), so a last-bit difference can be amplified on a hard
+    syndrome: at least 99 % of the columns must agree in best_decisions, converged flag AND iteration count, the
+    converged ones must reproduce their syndrome, and the rates must agree to 1 %."""
+    H, _, _ = codes.config_matrix(name)
+    _, syn = oracle.sample(H, per, 1357, 0, B)
+    ref = oracle.bpots_decode(H, per, mi, syn, T=T, C=C, nthreads=oracle.num_threads())
+    g = _run_bpots(pkg, H, per, mi, syn, T=T, C=C)
+    same = (g["errors"] == ref["errors"]).all(axis=0) & (g["converged"] == ref["converged"]) & (g["iters"] == ref["iters"])
+    assert same.mean() >= 0.99, (name, same.mean())
+    sat = ((H @ g["errors"]) % 2 == syn).all(axis=0)
+    assert (sat == g["converged"]).all()
+    assert abs(g["converged"].mean() - ref["converged"].mean()) <= 0.01
+
+
+def test_bpots_reference_test_cases(pkg, oracle):
+    """The reference's own BP-OTS tests re-expressed (test/test_bpots.jl): cycle matrices n = 4, 8, 16 with random syndromes
+    for several C (:56-114), the generic batchdecode! with a Matrix{Int} output (:139-153), a bool syndrome vector through
+    decode! (:155-167) -- every decoded error must reproduce its syndrome, exactly what those tests assert."""
+    rng = np.random.default_rng(5)
+    for n in (4, 8, 16):
+        H = _cycle_matrix(n)
+        errs = rng.integers(0, 2, (n, 64)).astype(np.uint8)
+        syn = (H @ errs) % 2
+        for C in (1.0, 2.0, 5.0, 10.0):
+            g = _run_bpots(pkg, H, 0.01, 100, syn, T=9, C=C, fmt=np.int64)
+            ref = oracle.bpots_decode(H, 0.01, 100, syn, T=9, C=C)
+            ok = ((H @ g["errors"]) % 2 == syn).all(axis=0)
+            ok_ref = ((H @ ref["errors"]) % 2 == syn).all(axis=0)
+            assert ok.mean() >= ok_ref.mean() - 0.05 and ok.mean() >= 0.9, (n, C, ok.mean(), ok_ref.mean())
+            assert (ok == g["converged"]).all()
+    H = _cycle_matrix(8)
+    dec = pkg.BPOTSDecoder(H, 0.01, 100, T=9, C=3.0)
+    e = np.zeros(8, dtype=bool)
+    e[:2] = True
+    syn = ((H @ e) % 2).astype(bool)
+    guess, conv = pkg.decode_b(dec, syn)
+    assert guess.dtype == np.int64 and conv and (((H @ guess) % 2).astype(bool) == syn).all()
+    assert pkg.reset_b(dec) is dec
+    dec.close()
