@@ -67,6 +67,8 @@ struct KernelParams {
     double *ratio;                // [B][n] or null
     int ratio_last_only;          // 1: write ratios only in iteration max_iters
     unsigned long long *counters; // [4] or null
+    const int *list;              // bp_smem_kernel: null, or the syndromes to decode (indices into the batch) ...
+    const int *list_count;        // ... and how many (device memory; written by first_iter_filter_kernel)
     unsigned long long *prof;     // bp_smem_kernel: null, or [8] phase cycle sums (check, wait B1, variable, flips, wait B2, done+emit, refill, iterations)
     // narrow tables (modes 0/1), copied to shared memory:
     const unsigned char *tables;  // global blob: rowptr u16[s+1] | colptr u16[n+1] | ve_off u32[E] | vflip u16[E]
@@ -140,14 +142,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most n (0..3) of the most recent groups are still in flight
+// wait until at most n (0..kMaxPrefetch) of the most recent groups are still in flight
+constexpr int kMaxPrefetch = 6;
 __device__ __forceinline__ void cp_async_wait_pending(int n)
 {
     switch (n) {
         case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
         case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
     }
 }
 

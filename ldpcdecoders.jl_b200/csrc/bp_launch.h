@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "bp_kernel.cuh"
+#include "bp_filter.cuh"
 
 namespace bp {
 
@@ -26,7 +27,8 @@ BP_DECLARE_MODE(0, 0, 2) BP_DECLARE_MODE(1, 0, 2) BP_DECLARE_MODE(2, 0, 2)
     cudaError_t smem_kernel_attrs_##V(int shape, int eb64, int smem_bytes, int threads, int *blocks_per_sm); \
     void smem_kernel_launch_##V(int shape, int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p); \
     cudaError_t smem_dual_attrs_##V(int eb64, int smem_bytes, int threads, int *blocks_per_sm);                  \
-    void smem_dual_launch_##V(int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);
+    void smem_dual_launch_##V(int eb64, int grid, int threads, int smem_bytes, cudaStream_t st, const KernelParams &p);       \
+    cudaError_t filter_setup_##V(const FilterSetup &q, cudaStream_t st);
 BP_DECLARE_SMEM(0) BP_DECLARE_SMEM(1) BP_DECLARE_SMEM(2)
 #undef BP_DECLARE_SMEM
 

@@ -135,12 +135,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
 
     // This CTA's queue: 32-syndrome chunks c, c+G, c+2G, ... of the batch (B < 2^31 - 32*G, host-checked).
     const int G = DUAL ? 2 * gridDim.x : gridDim.x, c = DUAL ? 2 * blockIdx.x + team : blockIdx.x;
-    const int Bn = static_cast<int>(p.B);
+    // (with a work list -- the syndromes the first-iteration filter left over -- queue entries index the list)
+    const int Bn = p.list ? __ldg(p.list_count) : static_cast<int>(p.B);
     const int nchunks = (Bn + 31) >> 5;
     const int Q = (c < nchunks) ? (((nchunks - c + G - 1) / G) << 5) : 0;
     auto sid_of = [&](int q) -> int {
         const int sid = (((q >> 5) * G + c) << 5) + (q & 31);
-        return (q < Q && sid < Bn) ? sid : -1;
+        if (!(q < Q && sid < Bn)) return -1;
+        return p.list ? __ldg(p.list + sid) : sid;
     };
     // wS moves staged syndromes into the lanes' own rows, wP prefetches the next queue window,
     // wO writes converged flags / iteration counts and keeps the counters.

@@ -1,4 +1,5 @@
 // bp_smem_inst.cuh -- body of one BP_VARIANT translation unit of the shared-memory-resident kernel (bp_smem.cuh).
+#define BP_FILTER_SETUP 1      // (before the first inclusion of bp_filter.cuh, which bp_launch.h pulls in)
 #include "bp_launch.h"
 #include "bp_smem.cuh"
 
@@ -49,6 +50,14 @@ void BPS_NAME(smem_kernel_launch_)(int shape, int eb64, int grid, int threads, i
     if (shape == kShape512x1) { if (eb64) smem_launch_one<512, 1, true>(grid, threads, smem_bytes, st, p); else smem_launch_one<512, 1, false>(grid, threads, smem_bytes, st, p); }
 }
 
+
+// ---- tables of the first-iteration filter, computed with this variant's node updates (bp_filter.cuh)
+cudaError_t BPS_NAME(filter_setup_)(const FilterSetup &q, cudaStream_t st)
+{
+    first_iter_check_table_kernel<<<1, 32, 0, st>>>(q);
+    first_iter_truth_table_kernel<<<(q.n + 127) / 128, 128, 0, st>>>(q);
+    return cudaGetLastError();
+}
 
 // ---- dual-team form: one CTA of 2 x W warps per SM (bp_smem_kernel<512, 1, EB64, PROF, true>)
 cudaError_t BPS_NAME(smem_dual_attrs_)(int eb64, int smem_bytes, int threads, int *bps)

