@@ -322,16 +322,25 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
             tick(2);
             if (cv) {
 #define BP_CASE(D)                                                                               \
-    while (f) {                                                                                  \
-        int b;                                                                                   \
-        if constexpr (EB64) b = __ffsll(static_cast<long long>(f)) - 1;                          \
-        else b = __ffs(static_cast<int>(f)) - 1;                                                 \
+    while (f) {                                  /* two flipped variables per trip: their table reads overlap */ \
+        int b0, b1;                                                                              \
+        if constexpr (EB64) b0 = __ffsll(static_cast<long long>(f)) - 1;                         \
+        else b0 = __ffs(static_cast<int>(f)) - 1;                                                \
         f &= f - 1;                                                                              \
-        const uint32_t fa = vflip_a + 2 * D * (vbase + b);                                       \
-        uint32_t ent[D];                                                                         \
-        _Pragma("unroll") for (int k = 0; k < D; ++k) ent[k] = lds_u16(fa + 2 * k);              \
+        const bool two = f != 0;                                                                 \
+        if constexpr (EB64) b1 = two ? __ffsll(static_cast<long long>(f)) - 1 : b0;              \
+        else b1 = two ? __ffs(static_cast<int>(f)) - 1 : b0;                                     \
+        f &= f - 1;                              /* (0 & -1 stays 0) */                          \
+        const uint32_t fa = vflip_a + 2 * D * (vbase + b0), fb = vflip_a + 2 * D * (vbase + b1); \
+        uint32_t ea[D], eb[D];                                                                   \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) ea[k] = lds_u16(fa + 2 * k);               \
+        _Pragma("unroll") for (int k = 0; k < D; ++k) eb[k] = lds_u16(fb + 2 * k);               \
         _Pragma("unroll") for (int k = 0; k < D; ++k)                                            \
-            asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(res_a + (ent[k] & ~127u)), "r"(1u << (ent[k] & 31u)) : "memory"); \
+            asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(res_a + (ea[k] & ~127u)), "r"(1u << (ea[k] & 31u)) : "memory"); \
+        if (two) {                                                                               \
+            _Pragma("unroll") for (int k = 0; k < D; ++k)                                        \
+                asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(res_a + (eb[k] & ~127u)), "r"(1u << (eb[k] & 31u)) : "memory"); \
+        }                                                                                        \
     }
                 BP_DEGREE_SWITCH(p.uni_vdeg, BP_CASE, ;)
 #undef BP_CASE
