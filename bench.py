@@ -418,6 +418,8 @@ def main():
                     help="phase timing of the shared-memory kernel (adds clock reads; not a bench value)")
     ap.add_argument("--max-ctas", type=int, default=0, dest="max_ctas", help="cap on resident CTAs per SM (experiments)")
     ap.add_argument("--lean", type=int, default=-1, help="family SMEM: 1 = round-2 kernel (default), 0 = general persistent kernel")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra ldpcb200_set_option pairs (experiments), e.g. --opt dual=1")
     ap.add_argument("--variant", default="exact", choices=["exact", "minsum", "fast"],
                     help="exact = reference-parity sum-product (headline); minsum = normalised min-sum (no reference equivalent)")
     args = ap.parse_args()
@@ -459,6 +461,9 @@ def main():
         opts["max_ctas_per_sm"] = args.max_ctas
     if args.kernel_profile:
         opts["kernel_profile"] = 1
+    for kv in args.opt:
+        k, v = kv.split("=", 1)
+        opts[k] = int(v)
     dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=[local], variant=args.variant, **opts)
     # a non-default torch stream: its handle is non-NULL, so the library launches on exactly the
     # stream the torch CUDA events are recorded on (NULL would mean "the handle's own stream")
