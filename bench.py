@@ -248,6 +248,9 @@ class DeviceRun:
         self.conv = torch.empty(self.tile, dtype=torch.uint8, device=dev)
         self.iters = torch.empty(self.tile, dtype=i32, device=dev)
         self.ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+        # the decoding kernel's own time: CUDA events recorded by the library on the launching stream around each launch
+        dec.set_option("time_kernels", 1)
+        self.kernel_s, self.kernel_launches = None, 0
 
     def sample(self, per):
         for t0 in range(0, self.B, self.tile):
@@ -272,6 +275,7 @@ class DeviceRun:
             if allreduce:
                 allreduce(self.ctr)
         (barrier or torch.cuda.synchronize)()
+        self.dec.kernel_time(reset=True)
         l0 = self.dec.launch_count()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         total = torch.zeros(4, dtype=torch.int64, device=self.dev)
@@ -287,6 +291,8 @@ class DeviceRun:
             total += self.ctr
         (barrier or torch.cuda.synchronize)()
         secs = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        kms, kl = self.dec.kernel_time(reset=True)
+        self.kernel_s, self.kernel_launches = kms / 1e3, kl       # summed over the timed steps
         return secs, total.cpu().numpy(), self.dec.launch_count() - l0
 
     def exact_match_frac_last_tile(self, per):
@@ -301,37 +307,56 @@ class DeviceRun:
         return float(score[0].item()) / bt
 
 
-def roofline_of(info, variant, E, SW, NW, B_per_step_gpu, units_per_step_gpu, step_s, clk_mhz, peaks, peaks_src, ncu):
-    """Roofline object of the dominant kernel (this rank's share, this rank's time)."""
+def roofline_of(info, variant, E, SW, NW, B_per_step_gpu, units_per_step_gpu, step_s, clk_mhz, peaks, peaks_src, ncu,
+                kernel_s=None, kernel_launches=0, filtered_per_step=0.0):
+    """Roofline object of the dominant kernel (this rank's share, this rank's time).
+    kernel_s: that kernel's own time per step (CUDA events on the launching stream around each of its launches, recorded by
+    the library: option time_kernels); filtered_per_step: syndromes the first-iteration filter finished (their single
+    iteration never reaches the decoding kernel).  achieved = algorithmic work of the kernel's launches / the kernel's time;
+    the whole-step figure (all kernels of the step, the filter's savings counted as work done) is reported next to it."""
     io_bytes = B_per_step_gpu * (SW * 4 + NW * 4 + 1 + 4)
     alg_bytes = units_per_step_gpu * 4.0 * E * 8.0 + io_bytes
+    k_s = kernel_s if kernel_s and kernel_s > 0 else step_s
+    k_units = max(units_per_step_gpu - filtered_per_step, 0.0)
+    timing = {"kernel_ms_per_step": 1e3 * k_s, "kernel_launches_per_step": kernel_launches, "step_ms": 1e3 * step_s,
+              "kernel_share_of_step": k_s / step_s, "kernel_units_per_step": k_units, "step_units_per_step": units_per_step_gpu,
+              "how": "CUDA events on the launching stream around every launch of the decoding kernel" if kernel_s else "step time (kernel not timed separately)"}
     traffic = None
     if ncu and ncu.get("dram_bytes_read") is not None and ncu.get("syndromes"):
-        # DRAM bytes of the profiled launch, scaled to this step's batch (both are linear in the batch)
-        traffic = (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) * B_per_step_gpu / float(ncu["syndromes"])
+        # DRAM bytes of the profiled launch, per launch of this run (both are linear in the launch's batch)
+        per_syn = (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) / float(ncu["syndromes"])
+        traffic = per_syn * B_per_step_gpu / max(kernel_launches, 1)
     if info["family"] == 1:
         slots = FP64_SLOTS[variant]
         peak = info["sm_count"] * FP64_LANES_PER_SM_CLK * clk_mhz * 1e6 / 1e12
-        ach = units_per_step_gpu * E * slots["model"] / step_s / 1e12
+        ach = k_units * E * slots["model"] / k_s / 1e12
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "frac_model_%d" % slots["model"]: ach / peak,
-                "frac_executed_%d" % slots["executed"]: units_per_step_gpu * E * slots["executed"] / step_s / 1e12 / peak,
-                "traffic": traffic,
-                "note": "shared-memory-resident kernel: bounded by the FP64 pipe, not HBM or tensor cores. achieved = (syndrome-iterations) x E x %d "
-                        "FP64-pipe issue slots per edge-iteration of the %s arithmetic per step / CUDA-event time; frac_executed counts the %d the kernel "
-                        "issues (comparable with ncu's sm__pipe_fp64_cycles_active); peak = %d SMs x 64 FP64 lanes/clk x median SM clock under load "
-                        "(%.0f MHz); one FLOP = one FP64 lane-instruction" % (
-                            slots["model"], "reference" if variant == "exact" else "min-sum", slots["executed"], info["sm_count"], clk_mhz),
+                "frac_executed_%d" % slots["executed"]: k_units * E * slots["executed"] / k_s / 1e12 / peak,
+                "whole_step_frac_model_%d" % slots["model"]: units_per_step_gpu * E * slots["model"] / step_s / 1e12 / peak,
+                "traffic": traffic, "timing": timing,
+                "note": "shared-memory-resident kernel: bounded by the FP64 pipe, not HBM or tensor cores. achieved = (syndrome, iteration) pairs the "
+                        "decoding kernel executed (the step's minus the single iterations the first-iteration filter finished with integer "
+                        "instructions) x E x %d FP64-pipe issue slots per edge-iteration of the %s arithmetic / the kernel's own CUDA-event time; "
+                        "frac_executed counts the %d the kernel issues (comparable with ncu's sm__pipe_fp64_cycles_active); whole_step_frac counts "
+                        "every iteration of the step against the step time (the filter's iterations cost no FP64 work, so it is a speed-up "
+                        "figure, not a pipe utilisation); peak = %d SMs x 64 FP64 lanes/clk x median SM clock under load (%.0f MHz); one FLOP = "
+                        "one FP64 lane-instruction" % (
+                            slots["model"], "reference" if variant == "exact" else variant, slots["executed"], info["sm_count"], clk_mhz),
                 "ncu": ncu,
                 "hbm_model": {"achieved_GBps": alg_bytes / step_s / 1e9, "peak_GBps": peaks["hbm_gbs"], "peak_source": peaks_src,
                               "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"],
                               "note": "4*E*8 B per syndrome-iteration if messages lived in HBM (they live in shared memory) + packed I/O"}}
     else:
-        roof = {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+        ach = alg_bytes / k_s / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "whole_step_frac": alg_bytes / step_s / 1e9 / peaks["hbm_gbs"],
+                "traffic": traffic, "timing": timing,
                 "algorithmic_bytes_per_step": alg_bytes,
-                "note": "algorithmic bytes = 4*E*8 per syndrome-iteration + packed I/O; peak = %s copy bandwidth; message store %d MB per GPU" % (
-                    peaks_src, info["message_bytes"] >> 20),
+                "algorithmic_bytes_per_launch": alg_bytes / max(kernel_launches, 1),
+                "note": "algorithmic bytes = 4*E*8 per syndrome-iteration + packed I/O of the kernel's launches / the kernel's own CUDA-event time; "
+                        "peak = %s copy bandwidth; message store %d MB per GPU; traffic = ncu dram bytes of one profiled launch scaled to this "
+                        "run's launch size" % (peaks_src, info["message_bytes"] >> 20),
                 "ncu": ncu}
     return roof
 
@@ -353,7 +378,8 @@ def sub_record(pkg, torch, dev, stream, name, per, B, tile, steps, warmup, peaks
         "syndrome_iterations_per_s": float(c[2]) / secs, "gpu_launches": int(launches),
         "kernel": {k: info[k] for k in ("family", "kernel_mode", "ctas_per_sm", "threads_per_cta", "message_bytes", "prefetch_distance", "kernel_rev")}}
     rec["roofline"] = roofline_of(info, variant, H.nnz, run.SW, run.NW, B, float(c[2]) / steps, secs / steps, clk_mhz, peaks, peaks_src,
-                                  ncu_record(name, variant, info["kernel_rev"]))
+                                  ncu_record(name, variant, info["kernel_rev"]),
+                                  kernel_s=run.kernel_s / steps, kernel_launches=run.kernel_launches / steps, filtered_per_step=float(c[3]) / steps)
     if oracle is not None:
         rec["cpu_baseline"] = cpu_baseline_leg(oracle, H, per, mi, SEED_E, cpu_budget, oracle.num_threads())
     dec.close()
@@ -508,7 +534,9 @@ def main():
     step_s = secs / args.steps
     clk_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     roof = roofline_of(info, args.variant, E, SW, NW, B, units_per_step_gpu, step_s, clk_mhz, peaks, peaks_src,
-                       ncu_record(args.workload, args.variant, info["kernel_rev"]))
+                       ncu_record(args.workload, args.variant, info["kernel_rev"]),
+                       kernel_s=run.kernel_s / args.steps, kernel_launches=run.kernel_launches / args.steps,
+                       filtered_per_step=float(c[3]) / args.steps / world)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -618,7 +646,8 @@ def main():
         ms_info = rms.info
         differ = int((rms.errw != errw_sp).any(dim=1).sum().item()) if run.tile >= B else None
         ms_roof = roofline_of(ms_info, "minsum", E, SW, NW, B, float(c2_[2]) / 3, secs2 / 3, clk_mhz, peaks, peaks_src,
-                              ncu_record(args.workload, "minsum", ms_info["kernel_rev"]))
+                              ncu_record(args.workload, "minsum", ms_info["kernel_rev"]),
+                              kernel_s=rms.kernel_s / 3, kernel_launches=rms.kernel_launches / 3, filtered_per_step=float(c2_[3]) / 3)
         line["minsum"] = {"value": float(c2_[0]) / secs2, "unit": UNIT, "per": per, "scale": 0.875,
                           "mean_iters": float(c2_[2]) / float(c2_[0]), "converged_frac": float(c2_[1]) / float(c2_[0]),
                           "exact_match_frac": rms.exact_match_frac_last_tile(per),

@@ -83,7 +83,7 @@ typedef struct {
 #define LDPCB200_CTR_DECODED     0  /* syndromes decoded */
 #define LDPCB200_CTR_CONVERGED   1  /* of which converged */
 #define LDPCB200_CTR_ITERATIONS  2  /* sum of executed BP iterations */
-#define LDPCB200_CTR_RESERVED    3
+#define LDPCB200_CTR_FILTERED    3  /* of which finished by the first-iteration filter (1 iteration each, no messages) */
 #define LDPCB200_NUM_COUNTERS    4
 
 /* OSD-0 statistics (ldpcb200_bposd_decode_batch / ldpcb200_osd0_device) */
@@ -235,6 +235,12 @@ int ldpcb200_selftest_division(int32_t device, int32_t mode, uint64_t n, uint64_
  * [3] residual-syndrome updates of flipped decisions, [4] wait at the second barrier, [5] syndrome re-check + outputs,
  * [6] refill -- and [7] the number of warp-iterations.  Synchronises the device.  Diagnostics, not part of the path. */
 int ldpcb200_kernel_profile(ldpcb200_t *h, int32_t dev_slot, int64_t *out8, int32_t reset);
+
+/* Duration of the decoding kernel itself (option "time_kernels" = 1 before the decodes): every launch of the persistent
+ * BP kernel is bracketed by CUDA events on the stream it is launched on; ms receives the sum of the elapsed times and
+ * launches their number since the last reset.  Synchronises the device.  bench.py's roofline uses it (the kernel's
+ * own time, not the step's).  Diagnostics, not part of the path. */
+int ldpcb200_kernel_time(ldpcb200_t *h, int32_t dev_slot, double *ms, int64_t *launches, int32_t reset);
 
 /* Number of kernels of this library launched through the handle so far (bench bookkeeping). */
 int ldpcb200_launch_count(const ldpcb200_t *h, int64_t *out);

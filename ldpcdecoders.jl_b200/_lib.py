@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libldpcb200.so")
+LIB_PATH = os.environ.get("LDPCB200_LIB") or os.path.join(HERE, "lib", "libldpcb200.so")   # (override: kernel experiments)
 
 OK, EINVAL, ECUDA, ENODEVICE, EUNSUPPORTED, ENOMEM = range(6)
 FMT_U8, FMT_I64, FMT_BITS, FMT_PACKED32, FMT_F64 = range(5)
@@ -25,6 +25,7 @@ SYMBOLS = [
     "ldpcb200_launch_count", "ldpcb200_selftest_division",
     "ldpcb200_bposd_decode_batch", "ldpcb200_osd0_device", "ldpcb200_kernel_profile",
     "ldpcb200_set_logicals", "ldpcb200_score_logical_device", "ldpcb200_set_per", "ldpcb200_sample_decode_score", "ldpcb200_bpots_decode_batch",
+    "ldpcb200_kernel_time",
 ]
 NUM_HARNESS_COUNTERS = 8
 HARNESS_FIELDS = ("shots", "converged", "iterations", "exact_matches", "syndrome_satisfied", "failures", "residual_weight", "osd_processed")
@@ -81,6 +82,7 @@ def load():
     lib.ldpcb200_set_per.argtypes = [vp, dbl]
     lib.ldpcb200_sample_decode_score.argtypes = [vp, i64, i64, u64, dbl, i32, ctypes.POINTER(i64)]
     lib.ldpcb200_kernel_profile.argtypes = [vp, i32, ctypes.POINTER(i64), i32]
+    lib.ldpcb200_kernel_time.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     lib.ldpcb200_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ldpcb200_selftest_division.argtypes = [i32, i32, u64, u64, ctypes.POINTER(u64)]   # mismatches[4]
     for name in SYMBOLS:

@@ -36,7 +36,7 @@ struct FilterParams {
     uint8_t *conv;
     int32_t *iters;
     int *list, *list_count;       // work list of the syndromes that need more than one iteration
-    unsigned long long *counters; // [0] decoded, [1] converged, [2] iterations (added for the syndromes finished here)
+    unsigned long long *counters; // [0] decoded, [1] converged, [2] iterations, [3] finished by this filter (added for the syndromes finished here)
 };
 
 constexpr int kFilterThreads = 128;
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kFilterThreads) first_iter_filter_kernel(const
         atomicAdd(p.counters + 0, n_conv);
         atomicAdd(p.counters + 1, n_conv);
         atomicAdd(p.counters + 2, n_conv);
+        atomicAdd(p.counters + 3, n_conv);      // LDPCB200_CTR_FILTERED
     }
 }
 #endif  // BP_FILTER_KERNEL

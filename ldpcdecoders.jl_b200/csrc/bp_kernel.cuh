@@ -38,6 +38,14 @@
 
 #include "bp_math.cuh"
 
+// mode 2 software pipelining of table / state loads from global memory (experiments: -DBP_M2_VAR_PIPE=0 etc.)
+#ifndef BP_M2_VAR_PIPE
+#define BP_M2_VAR_PIPE 0
+#endif
+#ifndef BP_M2_SYN_PRE
+#define BP_M2_SYN_PRE 0
+#endif
+
 namespace bp {
 
 // Node order inside the kernels is degree-sorted (host: build_graph): nodes of equal degree form
@@ -281,6 +289,18 @@ __device__ __forceinline__ double var_node_staged(uint32_t ra, unsigned char *ml
     return R;
 }
 
+// ... with the D slot offsets already in registers (mode 2 loads them one node ahead: they come from global memory)
+template <int D>
+__device__ __forceinline__ double var_node_staged_off(uint32_t ra, unsigned char *ml, const uint32_t (&v)[D], double p0, bool regular_p0)
+{
+    double m[D];
+    load_row<D>(m, ra);
+    const double R = var_update<D>(m, p0, regular_p0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) st_msg(ml + v[k], m[k]);
+    return R;
+}
+
 // Residual-syndrome update for the flipped variables of a lane when every variable has degree D:
 // variable j's D (word, bit) entries sit at vflip[j*D ..], no column-pointer reads.  `resid_lane`
 // points at this lane's column of the residual words ([word][32] layout).  Returns the change of
@@ -503,12 +523,18 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             islot = (islot + 1 == nslot) ? 0 : islot + 1;                                        \
         };                                                                                       \
         for (int t = 0; t < p.pd; ++t) issue();                                                  \
+        /* mode 2 keeps the syndrome in global memory (L2): the word of the NEXT check is fetched one trip ahead */ \
+        uint32_t sw_cur = 0, sw_nxt = 0;                                                         \
+        const bool sw_pre = BP_M2_SYN_PRE && !kStateShared && !p.perm_c;                                        \
+        if constexpr (!kStateShared) { if (sw_pre && i < end) sw_cur = syn[(i >> 5) * 32 + lane]; } \
         for (; i < end; i += W, ga += static_cast<size_t>(W) * (D * 256)) {                      \
             issue();                                                                             \
+            if constexpr (!kStateShared) { if (sw_pre && i + W < end) sw_nxt = syn[((i + W) >> 5) * 32 + lane]; } \
             cp_async_wait_pending(p.pd);                                                         \
             __syncwarp();                                                                        \
-            if (active) check_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, ga, syn_bit(i), fresh, p0, caux); \
+            if (active) check_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, ga, sw_pre ? ((sw_cur >> (i & 31)) & 1u) != 0u : syn_bit(i), fresh, p0, caux); \
             __syncwarp();                                                                        \
+            sw_cur = sw_nxt;                                                                     \
             cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                        \
         }                                                                                        \
         cp_async_wait_all();                                                                     \
@@ -687,24 +713,53 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         int jj = j, ie = eb + (j - first) * D, islot = 0, cslot = 0;                             \
+        /* mode 2 reads the slot offsets from global memory (L2 latency): the copy offsets of the next two nodes to be    \
+           issued (a0, a1: this half-warp's rows) and the store offsets of the next node to be computed (sn) are kept   \
+           in registers, loaded a trip or two before they are needed */                          \
+        constexpr bool kVarPipe = BP_M2_VAR_PIPE && !kStateShared;                               \
+        constexpr int HD = (D + 1) / 2;                                                          \
+        uint32_t a0[HD], a1[HD], sc[D], sn[D];                                                   \
+        auto ld_copy = [&](int jn, int en, uint32_t (&o)[HD]) {                                  \
+            _Pragma("unroll") for (int k = 0; k < D; k += 2) {                                   \
+                o[k / 2] = 0;                                                                    \
+                if (jn < end && k + (lane >> 4) < D) o[k / 2] = __ldg(p.g_ve_off + en + k + (lane >> 4)); \
+            }                                                                                    \
+        };                                                                                       \
+        auto ld_store = [&](int jn, int en, uint32_t (&o)[D]) {                                  \
+            _Pragma("unroll") for (int k = 0; k < D; ++k) o[k] = jn < end ? __ldg(p.g_ve_off + en + k) : 0u; \
+        };                                                                                       \
+        if constexpr (kVarPipe) { ld_copy(jj, ie, a0); ld_copy(jj + W, ie + W * D, a1); ld_store(j, ie, sc); } \
         auto issue = [&]() {                                                                     \
             if (jj < end) {                                                                      \
                 _Pragma("unroll") for (int k = 0; k < D; k += 2)                                 \
-                    if (k + (lane >> 4) < D)                                                     \
-                        cp_async16(ring_c + islot * p.ring_slot_bytes + (k + (lane >> 4)) * 256, cta_msg + off_at(ie + k + (lane >> 4))); \
+                    if (k + (lane >> 4) < D) {                                                   \
+                        uint32_t o_;                                                             \
+                        if constexpr (!kVarPipe) o_ = off_at(ie + k + (lane >> 4)); else o_ = a0[k / 2]; \
+                        cp_async16(ring_c + islot * p.ring_slot_bytes + (k + (lane >> 4)) * 256, cta_msg + o_); \
+                    }                                                                            \
             }                                                                                    \
             cp_async_commit();                                                                   \
             jj += W; ie += W * D;                                                                \
             islot = (islot + 1 == nslot) ? 0 : islot + 1;                                        \
+            if constexpr (kVarPipe) {                                                       \
+                _Pragma("unroll") for (int k = 0; k < HD; ++k) a0[k] = a1[k];                    \
+                ld_copy(jj + W, ie + W * D, a1);                                                 \
+            }                                                                                    \
         };                                                                                       \
         for (int t = 0; t < p.pd; ++t) issue();                                                  \
         TH vea = ve_handle(eb + (j - first) * D);                                                \
-        for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1)) {                    \
+        int ec = eb + (j - first) * D;                                                           \
+        for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1), ec += W * D) {       \
             issue();                                                                             \
+            if constexpr (kVarPipe) ld_store(j + W, ec + W * D, sn);                        \
             cp_async_wait_pending(p.pd);                                                         \
             __syncwarp();                                                                        \
-            if (active) record(j, i, var_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, msg_generic, vea, p0, regular_p0)); \
+            if (active) {                                                                        \
+                if constexpr (!kVarPipe) record(j, i, var_node_staged<D>(ring_l + cslot * p.ring_slot_bytes, msg_generic, vea, p0, regular_p0)); \
+                else record(j, i, var_node_staged_off<D>(ring_l + cslot * p.ring_slot_bytes, msg_generic, sc, p0, regular_p0)); \
+            }                                                                                    \
             __syncwarp();                                                                        \
+            if constexpr (kVarPipe) { _Pragma("unroll") for (int k = 0; k < D; ++k) sc[k] = sn[k]; } \
             cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                        \
         }                                                                                        \
         cp_async_wait_all();                                                                     \

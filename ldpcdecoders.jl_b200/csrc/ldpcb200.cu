@@ -164,6 +164,10 @@ struct DeviceCtx {
     bool f_ready = false;                                     // ... tables valid for the handle's current prior
     DevBuf lmask;                                         // logical operators: one 64-bit mask per variable (or empty)
     DevBuf hs_truth, hs_syn, hs_err, hs_conv, hs_iters, hs_ratio, hs_ctr, hs_sum;   // sampling + scoring harness tiles
+    // option "time_kernels": CUDA event pairs around every launch of the decoding kernel, on the launching stream
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime_events;
+    double ktime_ms = 0.0;
+    long long ktime_launches = 0;
     DevBuf tiny;            // small-batch host calls: one device block ...
     PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
@@ -202,6 +206,7 @@ struct ldpcb200 {
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     int opt_kernel_profile = 0;  // bp_smem_kernel adds per-phase SM cycles to the handle's profile block (ldpcb200_kernel_profile)
+    int opt_time_kernels = 0;    // bracket every launch of the decoding kernel with CUDA events (ldpcb200_kernel_time)
     int opt_max_ctas = 0;        // cap on resident CTAs per SM (0: whatever fits; experiments)
     int opt_lean = 1;            // family SMEM: use the round-2 kernel (bp_smem.cuh) when the code fits its envelope
     // resolved configuration
@@ -813,6 +818,23 @@ int filter_prepare(ldpcb200 *h, DeviceCtx &d, cudaStream_t st)
     return 0;
 }
 
+// Option "time_kernels": the decoding kernel's own duration, by CUDA events recorded on the launching stream right
+// before and after it (read back by ldpcb200_kernel_time once the stream is idle).
+struct KernelTimer {
+    DeviceCtx &d;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    KernelTimer(ldpcb200 *h, DeviceCtx &d_, cudaStream_t st_) : d(d_), st(st_)
+    {
+        if (!h->opt_time_kernels || d.ktime_events.size() >= 4096) return;
+        cudaEvent_t e0 = nullptr;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+        d.ktime_events.emplace_back(e0, e1);
+    }
+    ~KernelTimer() { if (e1) cudaEventRecord(e1, st); }
+};
+
 // Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
                      uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st,
@@ -926,6 +948,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
                 q.list = d.f_list.as<int>(); q.list_count = d.f_count.as<int>();
             }
             const long long groups = (Bl + 31) / 32;
+            KernelTimer timer(h, d, st);
             if (h->dual) {
                 const int gl = static_cast<int>(std::min<long long>((groups + 1) / 2, static_cast<long long>(d.sm_count) * h->ctas_per_sm));
                 if (h->variant == LDPCB200_VARIANT_MINSUM) bp::smem_dual_launch_1(h->eb64, gl, 2 * thr, h->smem_bytes, st, q);
@@ -940,6 +963,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             h->launches++;
         }
     } else {
+        KernelTimer timer(h, d, st);
         kernel_launch_dispatch(h->variant, h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
         h->launches++;
     }
@@ -1668,6 +1692,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     else if (k == "dual") h->opt_dual = value ? 1 : 0;
     else if (k == "contiguous_variables") h->opt_cv = value ? 1 : 0;
     else if (k == "kernel_profile") { h->opt_kernel_profile = value ? 1 : 0; return 0; }
+    else if (k == "time_kernels") { h->opt_time_kernels = value ? 1 : 0; return 0; }
     else if (k == "max_ctas_per_sm") h->opt_max_ctas = static_cast<int>(value);
     else if (k == "slots") h->opt_slots = static_cast<int>(value);   // accepted for compatibility, unused
     else return fail(LDPCB200_EINVAL, "unknown option '%s'", key);
@@ -2001,6 +2026,26 @@ int ldpcb200_kernel_profile(ldpcb200_t *h, int32_t dev_slot, int64_t *out8, int3
         if (reset) CU(cudaMemset(d.kprof.p, 0, 64));
     }
     for (int k = 0; k < 8; ++k) out8[k] = static_cast<int64_t>(v[k]);
+    return 0;
+}
+
+int ldpcb200_kernel_time(ldpcb200_t *h, int32_t dev_slot, double *ms, int64_t *launches, int32_t reset)
+{
+    if (!h || !ms || !launches || dev_slot < 0 || dev_slot >= static_cast<int>(h->dev.size())) return fail(LDPCB200_EINVAL, "bad argument");
+    DeviceCtx &d = h->dev[dev_slot];
+    CU(cudaSetDevice(d.device));
+    CU(cudaDeviceSynchronize());
+    for (auto &pr : d.ktime_events) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { d.ktime_ms += t; d.ktime_launches++; }
+        else cudaGetLastError();
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    d.ktime_events.clear();
+    *ms = d.ktime_ms;
+    *launches = d.ktime_launches;
+    if (reset) { d.ktime_ms = 0.0; d.ktime_launches = 0; }
     return 0;
 }
 

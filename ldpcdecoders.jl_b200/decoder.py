@@ -133,6 +133,14 @@ class BeliefPropagationDecoder:
         names = ("check", "wait_b1", "variable", "flips", "wait_b2", "done_emit", "refill", "warp_iterations")
         return dict(zip(names, [int(x) for x in out]))
 
+    def kernel_time(self, reset=True, dev_slot=0):
+        """(milliseconds, launches) of the decoding kernel itself since the last reset (option time_kernels=1):
+        CUDA events on the launching stream around every launch; see ldpcb200_kernel_time."""
+        ms = ctypes.c_double(0.0)
+        nl = ctypes.c_int64(0)
+        _lib.check(self._lib.ldpcb200_kernel_time(self._h, dev_slot, ctypes.byref(ms), ctypes.byref(nl), 1 if reset else 0))
+        return float(ms.value), int(nl.value)
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.ldpcb200_destroy(self._h)
