@@ -123,7 +123,7 @@ if json_out:
             return None
         u = v[1].lower()
         scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0,
-                 "nsecond": 1e-9}.get(u, 1.0)
+                 "nsecond": 1e-9, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
         return x * scale
     try:
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip()
