@@ -104,6 +104,7 @@ struct KernelParams {
     int pd, ring_slot_bytes, ring_warp_bytes;
     // shared-memory carve-up (byte offsets from the dynamic smem base)
     int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield, off_ring;
+    int off_sidq;             // bp_smem_kernel: [2][32] syndrome indices of the staged queue window
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     const uint32_t res0 = gbase + p.off_resid + lane * 4;         // residual buffers 0 / 1 of this lane
     const uint32_t res_sum = 2 * res0 + p.SW * 128;               // res0 + res1
     const uint32_t stage_a = gbase + p.off_stage;                 // [2][SW][32] staged syndromes of the queue window
+    const uint32_t sidq_a = gbase + p.off_sidq;                   // [2][32] their indices in the batch (-1: past the end)
     auto team_sync = [&]() {                                      // block barrier of this team
         if constexpr (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(W * 32) : "memory");
         else __syncthreads();
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     const int wS = 0, wP = (W > 1) ? 1 : 0, wO = (W > 2) ? 2 : 0;
     auto prefetch = [&](int q_head, int buf) {            // stage[buf][w][r] <- syndrome words of entry q_head + r
         const int sid = sid_of(q_head + lane);
+        // (a refill reads the index from here instead of repeating the dependent work-list load in every warp)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sidq_a + buf * 128 + lane * 4), "r"(sid) : "memory");
         if (sid >= 0) {
             const uint32_t *src = p.syn_words + static_cast<size_t>(sid) * p.SW;
             uint32_t *dst = reinterpret_cast<uint32_t *>(smem + goff + p.off_stage) + buf * p.SW * 32 + lane;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     auto refill = [&](uint32_t mask) {
         if ((mask >> lane) & 1u) {
             const int rank = __popc(mask & lt_mask);
-            sid = sid_of(q_head + rank);
+            sid = static_cast<int>(lds_u32(sidq_a + sbuf * 128 + rank * 4));
             active = sid >= 0;
             fresh = active;
             iter = 0;

@@ -268,7 +268,7 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
 }
 
 // shared-memory carve-up of bp_smem_kernel (bp_smem.cuh):
-//   messages | syn [SW][32] | resid [2][SW][32] | stage [2][SW][32] | tables | mbar
+//   messages | syn [SW][32] | resid [2][SW][32] | stage [2][SW][32] | sidq [2][32] | tables | mbar
 //   dual: the first four arrays twice (one group per team, group_stride apart), then tables | mbar | team flags
 int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p, bool dual = false)
 {
@@ -276,6 +276,7 @@ int smem_layout_lean(const ldpcb200 *h, bp::KernelParams &p, bool dual = false)
     p.off_syn = static_cast<int>(off);    off += h->SW * 128;
     p.off_resid = static_cast<int>(off);  off += 2 * h->SW * 128;      // per-lane double buffer
     p.off_stage = static_cast<int>(off);  off += 2 * h->SW * 128;      // double-buffered queue window
+    p.off_sidq = static_cast<int>(off);   off += 2 * 128;              // ... and the syndrome index of each of its entries
     p.off_nnz = p.off_efield = 0;
     p.group_stride = 0;
     if (dual) {
@@ -310,8 +311,12 @@ void build_tables(ldpcb200 *h, int cv_warps)
         h->cv_stride = align_up(h->cv_cpw * h->uni_vdeg * 4, 16);
         ve_bytes = cv_warps * h->cv_stride;
     }
-    const int o_col = align_up(static_cast<int>(2 * (s + 1)), 4);
-    const int o_ve = align_up(o_col + static_cast<int>(2 * (n + 1)), 16);
+    // (the contiguous-ownership layout is only read by bp_smem_kernel in its uniform-degree form, which needs neither
+    // rowptr nor colptr: those sections are left out -- on the gross code that is what makes room for the queue's
+    // staged syndrome indices next to two resident CTAs)
+    const bool ptrs = cv_warps <= 0;
+    const int o_col = ptrs ? align_up(static_cast<int>(2 * (s + 1)), 4) : 0;
+    const int o_ve = ptrs ? align_up(o_col + static_cast<int>(2 * (n + 1)), 16) : 0;
     const int o_fl = o_ve + ve_bytes;
     const int o_co = align_up(o_fl + static_cast<int>(2 * E), 4);
     const int o_vo = o_co + (h->perm_c ? static_cast<int>(2 * s) : 0);
@@ -320,8 +325,10 @@ void build_tables(ldpcb200 *h, int cv_warps)
     uint16_t *rp = reinterpret_cast<uint16_t *>(h->tables.data());
     uint16_t *cp = reinterpret_cast<uint16_t *>(h->tables.data() + o_col);
     uint32_t *ve = reinterpret_cast<uint32_t *>(h->tables.data() + o_ve);
-    for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->p_rowptr[i]);
-    for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->p_colptr[j]);
+    if (ptrs) {
+        for (int64_t i = 0; i <= s; ++i) rp[i] = static_cast<uint16_t>(h->p_rowptr[i]);
+        for (int64_t j = 0; j <= n; ++j) cp[j] = static_cast<uint16_t>(h->p_colptr[j]);
+    }
     uint16_t *fl = reinterpret_cast<uint16_t *>(h->tables.data() + o_fl);
     for (int64_t e = 0; e < E; ++e) {
         // residual-syndrome word (byte offset of its 128 B row) | bit: needs s <= 16384

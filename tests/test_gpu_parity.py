@@ -992,7 +992,10 @@ def test_first_iteration_filter_properties(pkg, oracle, codes):
             iters = np.zeros(B, dtype=np.int32)
             _, syn = oracle.sample(H, 0.01, 5, 0, B)
             _, success = pkg.batchdecode_b(dec, syn, errors, iters=iters)
-            outs.append((errors.copy(), success.copy(), iters.copy(), dec.last_counters.copy()))
+            ctr = dec.last_counters.copy()
+            # LDPCB200_CTR_FILTERED: syndromes the filter finished = those that report one iteration and converged
+            assert ctr[3] == (int(((iters == 1) & (success != 0)).sum()) if flt else 0), (variant, flt, ctr)
+            outs.append((errors.copy(), success.copy(), iters.copy(), ctr[:3]))
             dec.close()
         for a, b in zip(outs[0], outs[1]):
             assert np.array_equal(a, b), variant
