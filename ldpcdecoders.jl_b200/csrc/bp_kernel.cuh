@@ -523,6 +523,39 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
             ii += W; isrc += static_cast<size_t>(W) * (D * 256);                                 \
             islot = (islot + 1 == nslot) ? 0 : islot + 1;                                        \
         };                                                                                       \
+        /* two checks per trip (computed one after the other: the trip's bookkeeping is shared, not the registers) when \
+           the ring slot holds the rows of both */                                               \
+        if constexpr (D <= 6) if (2 * D * 256 <= p.ring_slot_bytes) {                            \
+            auto issue2 = [&]() {                                                                \
+                if (ii + W < end) {                                                              \
+                    _Pragma("unroll") for (int k = 0; k < 2 * D; k += 2) {                       \
+                        const int r = k + (lane >> 4);                                           \
+                        if (r < 2 * D)                                                           \
+                            cp_async16(ring_c + islot * p.ring_slot_bytes + r * 256,             \
+                                       isrc + (r < D ? r * 256 : static_cast<size_t>(W) * (D * 256) + (r - D) * 256)); \
+                    }                                                                            \
+                }                                                                                \
+                cp_async_commit();                                                               \
+                ii += 2 * W; isrc += static_cast<size_t>(2 * W) * (D * 256);                     \
+                islot = (islot + 1 == nslot) ? 0 : islot + 1;                                    \
+            };                                                                                   \
+            for (int t = 0; t < p.pd; ++t) issue2();                                             \
+            for (; i + W < end; i += 2 * W, ga += static_cast<size_t>(2 * W) * (D * 256)) {      \
+                issue2();                                                                        \
+                cp_async_wait_pending(p.pd);                                                     \
+                __syncwarp();                                                                    \
+                if (active) {                                                                    \
+                    const uint32_t ra_ = ring_l + cslot * p.ring_slot_bytes;                     \
+                    check_node_staged<D>(ra_, ga, syn_bit(i), fresh, p0, caux);                  \
+                    check_node_staged<D>(ra_ + D * 256, ga + static_cast<size_t>(W) * (D * 256), syn_bit(i + W), fresh, p0, caux); \
+                }                                                                                \
+                __syncwarp();                                                                    \
+                cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                    \
+            }                                                                                    \
+            cp_async_wait_all();                                                                 \
+            ii = i; islot = 0; cslot = 0;                                                        \
+            isrc = cta_msg + static_cast<size_t>(sb + (i - first) * D) * 256 + (lane & 15) * 16; \
+        }                                                                                        \
         for (int t = 0; t < p.pd; ++t) issue();                                                  \
         /* mode 2 keeps the syndrome in global memory (L2): the word of the NEXT check is fetched one trip ahead */ \
         uint32_t sw_cur = 0, sw_nxt = 0;                                                         \
@@ -747,8 +780,51 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
                 ld_copy(jj + W, ie + W * D, a1);                                                 \
             }                                                                                    \
         };                                                                                       \
-        for (int t = 0; t < p.pd; ++t) issue();                                                  \
         TH vea = ve_handle(eb + (j - first) * D);                                                \
+        /* Several variables per trip while the ring slot (sized for the widest node, times option ring_mult) holds the   \
+           rows of all of them: a fraction of the per-trip bookkeeping (group wait, warp syncs, slot rotation, loop      \
+           control) and more bytes in flight per warp */                                         \
+        auto multi = [&](auto nv_c) {                                                            \
+            constexpr int NV = decltype(nv_c)::value;                                            \
+            auto issue_n = [&]() {                                                               \
+                if (jj + (NV - 1) * W < end) {                                                   \
+                    _Pragma("unroll") for (int k = 0; k < NV * D; k += 2) {                      \
+                        const int r = k + (lane >> 4);                                           \
+                        if (r < NV * D)                                                          \
+                            cp_async16(ring_c + islot * p.ring_slot_bytes + r * 256,             \
+                                       cta_msg + off_at(ie + (r / D) * (W * D) + r % D));        \
+                    }                                                                            \
+                }                                                                                \
+                cp_async_commit();                                                               \
+                jj += NV * W; ie += NV * W * D;                                                  \
+                islot = (islot + 1 == nslot) ? 0 : islot + 1;                                    \
+            };                                                                                   \
+            const int step_n = W * D * (kStateShared ? 4 : 1);                                   \
+            for (int t = 0; t < p.pd; ++t) issue_n();                                            \
+            for (; j + (NV - 1) * W < end; j += NV * W, i += NV, vea += NV * step_n) {           \
+                issue_n();                                                                       \
+                cp_async_wait_pending(p.pd);                                                     \
+                __syncwarp();                                                                    \
+                if (active) {                                                                    \
+                    const uint32_t ra_ = ring_l + cslot * p.ring_slot_bytes;                     \
+                    double Rn[NV];                                                               \
+                    _Pragma("unroll") for (int v = 0; v < NV; ++v)                               \
+                        Rn[v] = var_node_staged<D>(ra_ + v * (D * 256), msg_generic, vea + v * step_n, p0, regular_p0); \
+                    _Pragma("unroll") for (int v = 0; v < NV; ++v) record(j + v * W, i + v, Rn[v]); \
+                }                                                                                \
+                __syncwarp();                                                                    \
+                cslot = (cslot + 1 == nslot) ? 0 : cslot + 1;                                    \
+            }                                                                                    \
+            cp_async_wait_all();                                                                 \
+            jj = j; ie = eb + (j - first) * D; islot = 0; cslot = 0;                             \
+        };                                                                                       \
+        if constexpr (!kVarPipe && D <= 3) {                                                     \
+            if (4 * D * 256 <= p.ring_slot_bytes) multi(std::integral_constant<int, 4>());       \
+        }                                                                                        \
+        if constexpr (!kVarPipe && D <= 6) {                                                     \
+            if (2 * D * 256 <= p.ring_slot_bytes) multi(std::integral_constant<int, 2>());       \
+        }                                                                                        \
+        for (int t = 0; t < p.pd; ++t) issue();                                                  \
         int ec = eb + (j - first) * D;                                                           \
         for (; j < end; j += W, ++i, vea += W * D * (kStateShared ? 4 : 1), ec += W * D) {       \
             issue();                                                                             \

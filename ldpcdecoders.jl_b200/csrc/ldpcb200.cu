@@ -204,6 +204,7 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
+    int opt_ring_mult = 0;       // ring slot = this many times the rows of the widest node (more nodes per loop trip of the HBM modes; 0 = auto)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     int opt_kernel_profile = 0;  // bp_smem_kernel adds per-phase SM cycles to the handle's profile block (ldpcb200_kernel_profile)
     int opt_time_kernels = 0;    // bracket every launch of the decoding kernel with CUDA events (ldpcb200_kernel_time)
@@ -259,7 +260,10 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
     // cp.async ring (modes 1/2): per warp pd+1 slots of one node's rows (max register degree)
     const int maxdeg = std::min(std::max(h->max_cdeg, h->max_vdeg), bp::kMaxRegDegree);
     p.pd = (mode >= 1) ? pd : 0;
-    p.ring_slot_bytes = std::max(maxdeg, 1) * 256;
+    // (a slot holds several nodes of a trip; measured best: two nodes' worth with tables in shared memory -- C4 0.87 -> 0.91
+    // of the HBM roofline -- one with tables in global memory, where a ring depth of 2 wins instead: C5 0.69 -> 0.74)
+    const int mult = h->opt_ring_mult > 0 ? h->opt_ring_mult : (mode == 1 ? 2 : 1);
+    p.ring_slot_bytes = std::max(maxdeg, 1) * 256 * mult;
     p.ring_warp_bytes = (p.pd + 1) * p.ring_slot_bytes;
     p.off_ring = static_cast<int>(off);
     if (p.pd > 0) off += static_cast<long long>(threads / 32) * p.ring_warp_bytes;
@@ -677,6 +681,7 @@ int configure(ldpcb200 *h)
     if (mode < 0) {
         family = LDPCB200_FAMILY_GLOBAL;
         const int pd_max = h->opt_pd >= 0 ? std::min(h->opt_pd, bp::kMaxPrefetch) : 3;
+        const int pd_max2 = h->opt_pd >= 0 ? pd_max : 2;     // mode 2 (two variables per trip): depth 2 measured best
         // HBM-bound: the depth of the cp.async ring matters more than the warp count, so take the
         // widest CTA (12, 10, 8 warps; two CTAs per SM) whose ring still reaches the full depth,
         // else the one with the deepest ring.  mode 1 (state + tables in shared memory) if it fits.
@@ -701,7 +706,7 @@ int configure(ldpcb200 *h)
                 }
             }
             if (m < 0) {
-                for (int pd = pd_max; pd >= 0 && m < 0; --pd) {
+                for (int pd = pd_max2; pd >= 0 && m < 0; --pd) {
                     need_w = smem_layout(h, 2, w * 32, f, false, pd, kw);
                     if (need_w <= budget) { m = 2; pd_fit = pd; }
                 }
@@ -710,7 +715,7 @@ int configure(ldpcb200 *h)
             if (m >= 0 && pd_fit > best_pd) {
                 best_pd = pd_fit; mode = m; warps = w; two = two_w; nfw = f; need = need_w; ef_global = efg; kp = kw;
             }
-            if (best_pd == pd_max) break;
+            if (best_pd == (mode == 2 ? pd_max2 : pd_max)) break;
         }
         if (mode < 0) return fail(LDPCB200_EUNSUPPORTED, "no kernel configuration fits in shared memory");
     }
@@ -1694,6 +1699,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
+    else if (k == "ring_mult") h->opt_ring_mult = static_cast<int>(std::min<int64_t>(std::max<int64_t>(value, 0), 4));
     else if (k == "lean") h->opt_lean = value ? 1 : 0;
     else if (k == "first_iteration_filter") { h->opt_filter = value ? 1 : 0; return 0; }
     else if (k == "dual") h->opt_dual = value ? 1 : 0;
