@@ -13,4 +13,17 @@ cudaError_t single_launch_1(int grid, int smem_bytes, cudaStream_t st, const Sin
     return cudaGetLastError();
 }
 
+cudaError_t grid_kernel_occupancy_1(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bp_grid_kernel<kGridThreads>, kGridThreads, 0);
+}
+
+cudaError_t grid_launch_1(int grid, cudaStream_t st, const GridParams &p)
+{
+    // cooperative launch: the runtime guarantees that all CTAs are co-resident (the kernel spins on a grid-wide barrier)
+    GridParams q = p;
+    void *args[] = {&q};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(bp_grid_kernel<kGridThreads>), dim3(grid), dim3(kGridThreads), args, 0, st);
+}
+
 }  // namespace bp

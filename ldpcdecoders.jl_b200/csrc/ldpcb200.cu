@@ -168,6 +168,8 @@ struct DeviceCtx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime_events;
     double ktime_ms = 0.0;
     long long ktime_launches = 0;
+    DevBuf gk_msg, gk_state;   // grid-wide small-batch kernel (bp_grid_kernel): messages [E], resid | dec | work[2] | bar[2]
+    int gk_blocks_per_sm = -1; // its co-resident CTAs per SM (-1: not asked yet, 0: unavailable)
     DevBuf tiny;            // small-batch host calls: one device block ...
     PinnedBuf tiny_host;    // ... mirrored by one pinned block (one copy each way, one synchronisation)
 };
@@ -204,6 +206,7 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
+    int opt_grid_kernel = 1;     // small batches of codes too large for the one-CTA kernel: the grid-wide cooperative kernel
     int opt_check_pair = 0;      // bp_smem_kernel: two checks per trip (check_update_pair)
     int opt_ring_mult = 0;       // ring slot = this many times the rows of the widest node (more nodes per loop trip of the HBM modes; 0 = auto)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
@@ -542,7 +545,7 @@ void destroy_device(DeviceCtx &d)
     cudaFree(d.d_tables); cudaFree(d.d_ve_off); cudaFree(d.d_vflip);
     cudaFree(d.d_p_rowptr); cudaFree(d.d_p_colptr); cudaFree(d.d_corig); cudaFree(d.d_vorig);
     if (d.set[1].stream) cudaStreamSynchronize(d.set[1].stream);
-    for (DevBuf *b : {&d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum, &d.f_vars, &d.f_edeg, &d.f_epos, &d.f_ctab, &d.f_list, &d.f_count, &d.lmask, &d.hs_truth, &d.hs_syn, &d.hs_err,
+    for (DevBuf *b : {&d.gk_msg, &d.gk_state, &d.msg, &d.state, &d.efield, &d.counters, &d.scratch, &d.osd_stats, &d.tiny, &d.kprof, &d.ctr_sum, &d.f_vars, &d.f_edeg, &d.f_epos, &d.f_ctab, &d.f_list, &d.f_count, &d.lmask, &d.hs_truth, &d.hs_syn, &d.hs_err,
                        &d.hs_conv, &d.hs_iters, &d.hs_ratio, &d.hs_ctr, &d.hs_sum}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
@@ -872,6 +875,42 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         const int64_t limit = h->opt_small_batch < 0 ? d.sm_count : h->opt_small_batch;
         const int off_syn = static_cast<int>((std::max<int64_t>(h->E, 1) * 8 + 15) / 16 * 16);
         const int smem = off_syn + 2 * h->SW * 4 + h->NW * 4;
+        // ... or, when the messages of one syndrome do not fit in an SM's shared memory, the whole grid per syndrome
+        // (cooperative launch, messages in L2): otherwise a lone decode! on a large code walks every edge on ONE lane
+        if (B <= limit && !h->big && smem > d.smem_optin && h->E > 0) {
+            if (d.gk_blocks_per_sm < 0) {
+                int coop = 0, bps = 0;
+                cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.device);
+                cudaError_t e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::grid_kernel_occupancy_1(&bps)
+                              : h->variant == LDPCB200_VARIANT_FAST32 ? bp::grid_kernel_occupancy_2(&bps) : bp::grid_kernel_occupancy_0(&bps);
+                if (e != cudaSuccess) { cudaGetLastError(); bps = 0; }
+                d.gk_blocks_per_sm = coop ? bps : 0;
+            }
+            const long long nodes = std::max(h->s, h->n);
+            const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(d.gk_blocks_per_sm) * d.sm_count,
+                                                                   (nodes + bp::kGridThreads - 1) / bp::kGridThreads));
+            // barrier counter: (2 * max_iters + 2) arrivals per syndrome and CTA, 32 bits
+            if (grid >= 1 && h->opt_grid_kernel && (2.0 * h->max_iters + 2.0) * static_cast<double>(B) * grid < 2.0e9) {
+                int rc;
+                const size_t st_bytes = static_cast<size_t>(h->SW + h->NW) * 4 + 16;
+                const bool fresh_state = d.gk_state.cap < st_bytes;
+                if ((rc = d.gk_msg.reserve(static_cast<size_t>(h->E) * 8)) || (rc = d.gk_state.reserve(st_bytes))) return rc;
+                if (fresh_state) CU(cudaMemsetAsync(d.gk_state.p, 0, st_bytes, st));      // counters start at zero; the kernel leaves them so
+                bp::GridParams q{};
+                q.s = static_cast<int>(h->s); q.n = static_cast<int>(h->n); q.E = static_cast<int>(h->E);
+                q.SW = h->SW; q.NW = h->NW; q.max_iters = h->max_iters; q.early_stop = h->opt_early_stop;
+                q.regular_p0 = h->regular_p0; q.ratio_last_only = ratio_last_only ? 1 : 0; q.p0 = h->p0; q.check_aux = h->ms_scale; q.B = B;
+                q.rowptr = d.d_rowptr; q.colptr = d.d_colptr; q.ve_slot = d.d_ve_slot; q.ve_chk = d.d_ve_chk;
+                q.syn_words = syn_words; q.err_words = err_words; q.conv = conv; q.iters = iters; q.ratio = ratio; q.counters = counters;
+                q.msg = d.gk_msg.as<double>();
+                q.resid = d.gk_state.as<uint32_t>(); q.dec = q.resid + h->SW;
+                q.work = reinterpret_cast<int *>(q.dec + h->NW); q.bar = reinterpret_cast<unsigned int *>(q.work + 2);
+                CU(h->variant == LDPCB200_VARIANT_MINSUM ? bp::grid_launch_1(grid, st, q)
+                   : h->variant == LDPCB200_VARIANT_FAST32 ? bp::grid_launch_2(grid, st, q) : bp::grid_launch_0(grid, st, q));
+                h->launches++;
+                return 0;
+            }
+        }
         if (B <= limit && !h->big && smem <= d.smem_optin && h->E * 8 < (1 << 30)) {
             bp::SingleParams q{};
             q.s = static_cast<int>(h->s); q.n = static_cast<int>(h->n); q.E = static_cast<int>(h->E);
@@ -1528,8 +1567,9 @@ int harness_on_device(ldpcb200 *h, DeviceCtx &d, int64_t first, int64_t shots, u
     CU(cudaSetDevice(d.device));
     cudaStream_t st = d.set[0].stream;
     int rc;
-    if ((rc = d.hs_ctr.reserve(LDPCB200_NUM_HARNESS_COUNTERS * 8))) return rc;
-    CU(cudaMemsetAsync(d.hs_ctr.p, 0, LDPCB200_NUM_HARNESS_COUNTERS * 8, st));
+    // [0..7] the harness counters, [8..11] the decode calls' own block (its slot 3 counts filter-finished syndromes)
+    if ((rc = d.hs_ctr.reserve((LDPCB200_NUM_HARNESS_COUNTERS + LDPCB200_NUM_COUNTERS) * 8))) return rc;
+    CU(cudaMemsetAsync(d.hs_ctr.p, 0, (LDPCB200_NUM_HARNESS_COUNTERS + LDPCB200_NUM_COUNTERS) * 8, st));
     if (shots > 0) {
         // tile: bounded by 64 MB of packed rows (and 1 GB of posterior ratios when OSD follows)
         int64_t tile = std::max<int64_t>(32, (64ll << 20) / (static_cast<int64_t>(h->SW + 2 * h->NW) * 4 + 5));
@@ -1560,7 +1600,7 @@ int harness_on_device(ldpcb200 *h, DeviceCtx &d, int64_t first, int64_t shots, u
             h->launches += 2;
             const bool want_ratio = osd && h->max_iters > 0;
             rc = decode_on_device(h, d, bt, d.hs_syn.as<uint32_t>(), d.hs_err.as<uint32_t>(), d.hs_conv.as<uint8_t>(), d.hs_iters.as<int32_t>(),
-                                  want_ratio ? d.hs_ratio.as<double>() : nullptr, ctr, st, h->opt_osd_order == 0);
+                                  want_ratio ? d.hs_ratio.as<double>() : nullptr, ctr + LDPCB200_NUM_HARNESS_COUNTERS, st, h->opt_osd_order == 0);
             if (rc) return rc;
             if (osd) {
                 if (h->max_iters <= 0) {
@@ -1581,6 +1621,7 @@ int harness_on_device(ldpcb200 *h, DeviceCtx &d, int64_t first, int64_t shots, u
             h->launches++;
             CU(cudaGetLastError());
         }
+        CU(cudaMemcpyAsync(ctr, ctr + LDPCB200_NUM_HARNESS_COUNTERS, 3 * 8, cudaMemcpyDeviceToDevice, st));   // decoded, converged, iterations
         if (osd) CU(cudaMemcpyAsync(ctr + 7, d.osd_stats.p, 8, cudaMemcpyDeviceToDevice, st));
     }
     unsigned long long hc[LDPCB200_NUM_HARNESS_COUNTERS];
@@ -1700,6 +1741,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "grid_kernel") { h->opt_grid_kernel = value ? 1 : 0; return 0; }
     else if (k == "check_pair") { h->opt_check_pair = value ? 1 : 0; return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "ring_mult") h->opt_ring_mult = static_cast<int>(std::min<int64_t>(std::max<int64_t>(value, 0), 4));

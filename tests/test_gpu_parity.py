@@ -23,8 +23,11 @@ def run_gpu(pkg, H, per, max_iters, syn, family=0, want_ratio=False, fmt="u8", *
     _, success = pkg.batchdecode_b(dec, np.asfortranarray(syn.astype(dt)), errors, iters=iters, posterior_ratio=ratio)
     info = dec.info()
     counters = dec.last_counters.copy()
+    launches = dec.launch_count()
+    persistent_launches = dec.kernel_time()[1]
     dec.close()
-    return dict(errors=errors.astype(np.uint8), converged=success, iters=iters, ratio=ratio, info=info, counters=counters)
+    return dict(errors=errors.astype(np.uint8), converged=success, iters=iters, ratio=ratio, info=info, counters=counters, launches=launches,
+                persistent_launches=persistent_launches)
 
 
 def assert_same(g, r, want_ratio=False):
@@ -84,14 +87,41 @@ def test_parity_c5_large_code(pkg, oracle, codes):
     B = 40
     _, syn = oracle.sample(H, per, 12345, 0, B)
     ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads())
-    g = run_gpu(pkg, H, per, mi, syn)
+    g = run_gpu(pkg, H, per, mi, syn, grid_kernel=0)         # (small batches would otherwise take the grid-wide kernel)
     assert g["info"]["family"] == GLOBAL
     assert_same(g, ref)
     # harder channel: some syndromes must run many iterations
     _, syn = oracle.sample(H, 0.07, 777, 0, 16)
     ref = oracle.batch_decode(H, 0.07, mi, syn, nthreads=oracle.num_threads())
-    g = run_gpu(pkg, H, 0.07, mi, syn, slots=32)
+    g = run_gpu(pkg, H, 0.07, mi, syn, slots=32, grid_kernel=0)
     assert_same(g, ref)
+
+
+@pytest.mark.parametrize("variant", ["exact", "minsum"])
+def test_grid_kernel_small_batches_of_a_large_code(pkg, oracle, codes, variant):
+    """decode! / a handful of columns on a code whose messages do not fit in one SM's shared memory (n = 100 002) run on
+    the grid-wide cooperative kernel (bp_single.cuh: bp_grid_kernel): bit-identical to the oracle, to the persistent
+    kernel, across repeated launches (its barrier counters must come back to zero), with posterior ratios."""
+    H, per, mi = codes.config_matrix("C5")
+    for B, p_ch, seed in ((1, per, 5), (3, 0.07, 6), (20, 0.05, 7)):
+        _, syn = oracle.sample(H, p_ch, seed, 0, B)
+        ref = oracle.batch_decode(H, p_ch, mi, syn, nthreads=oracle.num_threads(), want_ratio=(B == 3), variant=variant)
+        g = run_gpu(pkg, H, p_ch, mi, syn, want_ratio=(B == 3), variant=variant, time_kernels=1)
+        assert g["persistent_launches"] == 0                   # (only launches of the persistent kernels are timed)
+        assert_same(g, ref, want_ratio=(B == 3))
+        if B == 3:
+            g0 = run_gpu(pkg, H, p_ch, mi, syn, want_ratio=True, variant=variant, time_kernels=1, grid_kernel=0)
+            assert g0["persistent_launches"] == 1
+            assert_same(g0, ref, want_ratio=True)
+    # one decoder, many calls: single decode! (host vectors in and out) and forced iterations
+    dec = pkg.BeliefPropagationDecoder(H, 0.05, 6, variant=variant)
+    _, syn = oracle.sample(H, 0.05, 8, 0, 4)
+    ref = oracle.batch_decode(H, 0.05, 6, syn, nthreads=oracle.num_threads(), variant=variant)
+    for rep in range(2):
+        for c in range(4):
+            guess, conv = pkg.decode_b(dec, syn[:, c])
+            assert np.array_equal(np.asarray(guess != 0, dtype=np.uint8), ref["errors"][:, c]) and bool(conv) == bool(ref["converged"][c])
+    dec.close()
 
 
 def test_auto_family_selection(pkg, codes):
@@ -455,7 +485,7 @@ def test_minsum_large_code_and_scale_option(pkg, oracle, codes):
     H, per, mi = codes.config_matrix("C5")
     _, syn = oracle.sample(H, per, 99, 0, 24)
     ref = oracle.batch_decode(H, per, mi, syn, nthreads=oracle.num_threads(), variant="minsum")
-    g = run_gpu_variant(pkg, H, per, mi, syn, "minsum")
+    g = run_gpu_variant(pkg, H, per, mi, syn, "minsum", grid_kernel=0)
     assert g["info"]["kernel_mode"] == 2
     assert np.array_equal(g["errors"], ref["errors"]) and np.array_equal(g["iters"], ref["iters"])
     # plain (unnormalised) min-sum through the scale option

@@ -51,3 +51,44 @@ for B in (1, 100):
                                           a.elapsed_time(b_) / 50 * 1e3))
     print("C1 device-resident decode of %d syndrome(s): %s" % (B, "; ".join(out)))
 dec.close()
+
+# ---- the same question for a LARGE code (C5, n = 100 002: the messages of one syndrome, 2.4 MB, do not fit in an SM's
+# shared memory): grid-wide cooperative kernel vs one lane of the persistent kernel, device-resident, early stop
+H, per, mi = pkg.codes.config_matrix("C5")
+dec = pkg.BeliefPropagationDecoder(H, per, mi)
+info = dec.info()
+SW, NW = info["syn_words"], info["err_words"]
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+st = stream.cuda_stream
+for B in (1, 16):
+    truth = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    synw = torch.empty((B, SW), dtype=torch.int32, device=dev)
+    errw = torch.empty((B, NW), dtype=torch.int32, device=dev)
+    conv = torch.empty(B, dtype=torch.uint8, device=dev)
+    its = torch.empty(B, dtype=torch.int32, device=dev)
+    dec.sample_device(B, 0, 2024, per, truth.data_ptr(), synw.data_ptr(), stream=st)
+    out = []
+    for gk, reps in ((1, 20), (0, 3)):
+        dec.set_option("grid_kernel", gk)
+        for _ in range(2):
+            dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), its.data_ptr(), None, None, stream=st)
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            dec.decode_device(B, synw.data_ptr(), errw.data_ptr(), conv.data_ptr(), its.data_ptr(), None, None, stream=st)
+        b_.record(stream)
+        torch.cuda.synchronize()
+        out.append("%s %.1f us (mean iterations %.2f)" % ("grid-wide kernel" if gk else "persistent kernel", a.elapsed_time(b_) / reps * 1e3,
+                                                          float(its.float().mean().item())))
+    print("C5 device-resident decode of %d syndrome(s): %s" % (B, "; ".join(out)))
+syn1 = oracle.sample(H, per, 2024, 0, 4)[1]
+for b in range(2):
+    pkg.decode_b(dec.__class__(H, per, mi) if False else dec, syn1[:, b])
+dec.set_option("grid_kernel", 1)
+t0 = time.perf_counter()
+for b in range(4):
+    pkg.decode_b(dec, syn1[:, b])
+print("C5 single decode! through the Python mirror (host vectors in/out, posterior ratios back): %.1f us per call" % ((time.perf_counter() - t0) / 4 * 1e6))
+dec.close()
