@@ -121,7 +121,16 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   unconverged; 1..12 = the order-O exhaustive search of belief_propagation_osd.jl:127-209 on EVERY syndrome, as the
  *   reference's decode! does for osd_order > 0),
  *   "ratio_last_only" (ldpcb200_decode_device writes d_posterior_ratio only in iteration max_iters: all an OSD
- *   stage needs, since it only reads the ratios of syndromes that did not converge; default 0). */
+ *   stage needs, since it only reads the ratios of syndromes that did not converge; default 0),
+ *   "grid_kernel" (1, default: small batches of codes whose messages exceed one SM's shared memory run on the grid-wide
+ *   cooperative kernel, one syndrome at a time over all SMs; 0 = persistent kernel),
+ *   "first_iteration_filter" (1, default: family SMEM evaluates iteration 1 of every syndrome from per-variable truth
+ *   tables and decodes only the syndromes that did not converge there; results are identical either way),
+ *   "ring_mult" (HBM modes: ring slot = this many times the rows of the widest node, i.e. nodes per loop trip; 0 = auto),
+ *   "stage_pageable" (1, default: pageable host buffers are staged through pinned blocks), "nccl" (1, default: a
+ *   multi-device handle sums its counters with ncclAllReduce), "time_kernels" (see ldpcb200_kernel_time),
+ *   "kernel_profile" (see ldpcb200_kernel_profile), "osd_profile"; experiments that measured no gain and stay off:
+ *   "dual" (two teams per CTA), "check_pair" (two checks per loop trip), "max_ctas_per_sm". */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);
 
 /* Replaces batchdecode!(decoder, syndromes, errors, success)
