@@ -1,15 +1,15 @@
+# Final 1-GPU evidence run of a round: test-suite, smoke, the default bench line, launch list, ncu captures.
 set -x
-python __graft_entry__.py smoke 2>&1 | tail -6
-python bench.py --steps 5 --warmup 3 > gpurun_out/f_c3.json 2> gpurun_out/f_c3.err; tail -c 300 gpurun_out/f_c3.err
-python bench.py --workload C4 --steps 3 --warmup 3 > gpurun_out/f_c4.json 2> gpurun_out/f_c4.err; tail -c 300 gpurun_out/f_c4.err
-python bench.py --workload C5 --steps 3 --warmup 3 --no-sweep > gpurun_out/f_c5.json 2> gpurun_out/f_c5.err; tail -c 300 gpurun_out/f_c5.err
-python bench.py --workload C2 --steps 5 --warmup 3 --no-sweep > gpurun_out/f_c2.json 2> gpurun_out/f_c2.err; tail -c 300 gpurun_out/f_c2.err
+python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee gpurun_out/f_pytest.txt
+python __graft_entry__.py smoke 2>&1 | tail -4 | tee gpurun_out/f_smoke.txt
+python bench.py --steps 5 --warmup 3 > gpurun_out/f_default.json 2> gpurun_out/f_default.err; tail -c 300 gpurun_out/f_default.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/f_ref.json 2> gpurun_out/f_ref.err; tail -c 300 gpurun_out/f_ref.err
 python bench.py --steps 2 --warmup 3 --no-cpu --no-sweep > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-sweep > gpurun_out/f_ncu.log 2>&1
-for f in gpurun_out/f_c*.json; do python -c "
-import json,sys
-d=json.load(open('$f')); print('$f', d['value'], d['e2e']['value'], d['roofline']['bound'], round(d['roofline']['frac'],3), d.get('cpu_baseline',{}).get('value'))"; done
-# ncu --set full capture of the headline kernel (report stays on the box; only the text summary comes back)
-timeout 700 ncu --set full --clock-control none --import-source on -k regex:bp_persistent -c 1 -o /tmp/c3 python bench.py --batch 2000000 --steps 1 --warmup 1 --no-cpu --no-sweep --no-e2e > /dev/null 2> gpurun_out/f_ncu_c3.err
-python tools/ncu_summary.py /tmp/c3.ncu-rep /tmp/c3_sass.txt > gpurun_out/f_c3_ncu.txt 2>&1
-head -30 gpurun_out/f_c3_ncu.txt | cut -c1-130
+python -c "
+import json
+d=json.load(open('gpurun_out/f_default.json')); r=d['roofline']
+print('C3', d['value'], d['e2e']['value'], r['frac'], r.get('frac_executed_21'), r['timing']['kernel_share_of_step'], r['traffic'])
+for k in ('config_C4_hgp1600_10M','config_C5_gallager100k_1M'):
+    x=d[k]; print(k, x['value'], x['roofline']['frac'], x['roofline']['traffic'], x['roofline']['algorithmic_bytes_per_launch'])
+"
+bash tools/ncu_capture.sh r2 ${1:-unknown} C3 C4 C5
