@@ -150,6 +150,8 @@ struct DeviceCtx {
         cudaStream_t stream = nullptr;
         DevBuf raw_in, raw_out, syn_words, err_words, conv, iters, ratio;
         DevBuf osd_list, osd_ctl;            // OSD-0: unconverged list, {count, queue}
+        DevBuf f_list, f_count;              // first-iteration filter: this set's own work list, so that the decoding kernels
+                                             // of consecutive chunks may overlap (shared-memory kernel: nothing else is shared)
         // pageable caller memory is staged through pinned blocks so that the copies stay asynchronous: the chunk's
         // input is gathered into pin_in by the host thread while the GPU works on the previous chunk; outputs land in
         // pin_out and are handed to the caller (`pending`) when this set comes round again
@@ -206,6 +208,7 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
+    int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap
     int opt_grid_kernel = 1;     // small batches of codes too large for the one-CTA kernel: the grid-wide cooperative kernel
     int opt_check_pair = 0;      // bp_smem_kernel: two checks per trip (check_update_pair)
     int opt_ring_mult = 0;       // ring slot = this many times the rows of the widest node (more nodes per loop trip of the HBM modes; 0 = auto)
@@ -549,7 +552,7 @@ void destroy_device(DeviceCtx &d)
                        &d.hs_conv, &d.hs_iters, &d.hs_ratio, &d.hs_ctr, &d.hs_sum}) b->release();
     d.tiny_host.release();
     for (auto &S : d.set)
-        for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl})
+        for (DevBuf *b : {&S.raw_in, &S.raw_out, &S.syn_words, &S.err_words, &S.conv, &S.iters, &S.ratio, &S.osd_list, &S.osd_ctl, &S.f_list, &S.f_count})
             b->release();
     for (auto &S : d.set) { S.pin_in.release(); S.pin_out.release(); }
     if (d.decode_done) cudaEventDestroy(d.decode_done);
@@ -829,6 +832,7 @@ int filter_prepare(ldpcb200 *h, DeviceCtx &d, cudaStream_t st)
     cudaError_t e = h->variant == LDPCB200_VARIANT_MINSUM ? bp::filter_setup_1(q, st)
                   : h->variant == LDPCB200_VARIANT_FAST32 ? bp::filter_setup_2(q, st) : bp::filter_setup_0(q, st);
     if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "first-iteration tables: %s", cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(st));              // (other streams of the device read the tables from now on)
     h->launches += 2;
     d.f_ready = true;
     return 0;
@@ -854,8 +858,9 @@ struct KernelTimer {
 // Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
                      uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st,
-                     bool ratio_last_only = false)
+                     bool ratio_last_only = false, DeviceCtx::StageSet *set = nullptr)
 {
+    DevBuf &f_list = set ? set->f_list : d.f_list, &f_count = set ? set->f_count : d.f_count;
     if (B <= 0) return 0;
     CU(cudaSetDevice(d.device));
     if (h->max_iters <= 0) {
@@ -986,19 +991,19 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             q.syn_words = syn_words + b0 * h->SW; q.err_words = err_words + b0 * h->NW; q.conv = conv + b0;
             q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
             if (filter) {
-                if ((rc = d.f_list.reserve(static_cast<size_t>(Bl) * 4)) || (rc = d.f_count.reserve(16))) return rc;
-                CU(cudaMemsetAsync(d.f_count.p, 0, 16, st));
+                if ((rc = f_list.reserve(static_cast<size_t>(Bl) * 4)) || (rc = f_count.reserve(16))) return rc;
+                CU(cudaMemsetAsync(f_count.p, 0, 16, st));
                 bp::FilterParams f{};
                 f.s = static_cast<int>(h->s); f.n = static_cast<int>(h->n); f.SW = h->SW; f.NW = h->NW; f.B = Bl;
                 f.vars = d.f_vars.as<bp::FilterVar>();
                 f.syn_words = q.syn_words; f.err_words = q.err_words; f.conv = q.conv; f.iters = q.iters;
-                f.list = d.f_list.as<int>(); f.list_count = d.f_count.as<int>(); f.counters = counters;
+                f.list = f_list.as<int>(); f.list_count = f_count.as<int>(); f.counters = counters;
                 const int fsmem = (2 * h->SW + h->NW) * 32 * 4 * bp::kFilterWarps;
                 const int fgrid = static_cast<int>(std::min<int64_t>((Bl + bp::kFilterThreads - 1) / bp::kFilterThreads, static_cast<int64_t>(d.sm_count) * 16));
                 if (fsmem > 48 * 1024) CU(cudaFuncSetAttribute(bp::first_iter_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));
                 bp::first_iter_filter_kernel<<<fgrid, bp::kFilterThreads, fsmem, st>>>(f);
                 h->launches++;
-                q.list = d.f_list.as<int>(); q.list_count = d.f_count.as<int>();
+                q.list = f_list.as<int>(); q.list_count = f_count.as<int>();
             }
             const long long groups = (Bl + 31) / 32;
             KernelTimer timer(h, d, st);
@@ -1328,7 +1333,9 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     const bool pg_out = h->opt_stage_pageable && is_pageable(errors);
     const bool pg_conv = h->opt_stage_pageable && is_pageable(converged), pg_iters = h->opt_stage_pageable && is_pageable(iters),
                pg_ratio = h->opt_stage_pageable && is_pageable(ratio);
-    const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : 4);
+    // (where the decoding kernels of consecutive chunks may overlap -- shared-memory kernel -- a chunk's tail of slow
+    //  syndromes costs nothing, and six chunks measured best: C3 10 M BitMatrix 3.49e8 -> 3.65e8 syndromes/s end to end)
+    const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : ((h->lean && !ots && h->opt_overlap_chunks) ? 6 : 4));
     int64_t CH = h->opt_chunk > 0 ? h->opt_chunk
                                   : std::max<int64_t>({(Bd + nchunk_target - 1) / nchunk_target, 32768, 2 * static_cast<int64_t>(h->slots)});
     CH = std::min<int64_t>(CH, static_cast<int64_t>(budget / std::max(per_syn, 1.0)));
@@ -1417,7 +1424,10 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
             return fail(LDPCB200_EINVAL, "unsupported syndrome format %d", syn_fmt);
         }
         // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
-        if (have_prev_decode) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
+        // (the shared-memory kernel keeps everything on chip and its filter list is per set: there the next chunk's kernel
+        //  may start while the previous one is still finishing its slowest syndromes)
+        const bool ordered = !(h->lean && !osd && !ots && h->opt_overlap_chunks);
+        if (have_prev_decode && ordered) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
         // (OSD-0 only reads the ratios of unconverged syndromes: those of iteration max_iters; a higher order post-processes
         //  every syndrome, so the ratios of each syndrome's own last iteration are needed)
         if (ots)
@@ -1425,7 +1435,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         else
         rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
                               (ratio || (osd && h->max_iters > 0)) ? S.ratio.as<double>() : nullptr,
-                              d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0);
+                              d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0, &S);
         if (rc) return rc;
         CU(cudaEventRecord(d.decode_done, st));
         have_prev_decode = true;
@@ -1741,6 +1751,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "overlap_chunks") { h->opt_overlap_chunks = value ? 1 : 0; return 0; }
     else if (k == "grid_kernel") { h->opt_grid_kernel = value ? 1 : 0; return 0; }
     else if (k == "check_pair") { h->opt_check_pair = value ? 1 : 0; return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
