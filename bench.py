@@ -444,6 +444,9 @@ def main():
                     help="phase timing of the shared-memory kernel (adds clock reads; not a bench value)")
     ap.add_argument("--max-ctas", type=int, default=0, dest="max_ctas", help="cap on resident CTAs per SM (experiments)")
     ap.add_argument("--lean", type=int, default=-1, help="family SMEM: 1 = round-2 kernel (default), 0 = general persistent kernel")
+    ap.add_argument("--strong", action="store_true",
+                    help="under torchrun: ONE batch of the workload's size split over the ranks (sharding.shard_range) instead of "
+                         "one batch per rank: strong scaling of the one-process-per-GPU form")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="extra ldpcb200_set_option pairs (experiments), e.g. --opt dual=1")
     ap.add_argument("--variant", default="exact", choices=["exact", "minsum", "fast"],
@@ -504,9 +507,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    allreduce = pkg.sharding.allreduce_counters if world > 1 else None     # the path's only collective
+    B_total, first = B * world, rank * B                   # weak scaling: every rank owns global syndromes [r*B, (r+1)*B)
+    if args.strong and world > 1:                          # strong scaling: one batch, contiguous 32-aligned column ranges
+        B_total = B
+        first, hi = pkg.sharding.shard_range(B_total, rank, world)
+        B = hi - first
     # ---- synthetic inputs, resident in HBM; shard r owns global syndromes [r*B, (r+1)*B)
-    run = DeviceRun(torch, dev, stream, dec, B, tile, first=rank * B)
+    run = DeviceRun(torch, dev, stream, dec, B, tile, first=first)
     info = run.info
     SW, NW = run.SW, run.NW
     flush = None
@@ -539,9 +547,12 @@ def main():
                        filtered_per_step=float(c[3]) / args.steps / world)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, H, per, mi, B, {"tile": run.tile} if run.tile < B else None),
+            "config": config_dict(args, H, per, mi, B, dict({"tile": run.tile} if run.tile < B else {}, batch_total=B_total,
+                                                             split="one batch split over the ranks (strong)" if (args.strong and world > 1)
+                                                             else "one batch per rank (weak)")),
             "mean_iters": mean_iters, "converged_frac": conv_frac, "exact_match_frac": exact_frac,
             "syndrome_iterations_per_s": float(c[2]) / secs,
             "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
