@@ -105,7 +105,6 @@ struct KernelParams {
     // shared-memory carve-up (byte offsets from the dynamic smem base)
     int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield, off_ring;
     int off_sidq;             // bp_smem_kernel: [2][32] syndrome indices of the staged queue window
-    int check_pair;           // bp_smem_kernel: two checks per loop trip, division chains interleaved (option "check_pair")
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

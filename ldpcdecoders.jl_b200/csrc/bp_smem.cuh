@@ -216,35 +216,11 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         token_wait();
         if (active) {
             int i = warp;
-            auto syn_of = [&](int ik) -> bool {           // syndrome bit of the kernels' ik-th check
-                const int io = p.perm_c ? static_cast<int>(lds_u16(corig_a + 2 * ik)) : ik;
-                return (lds_u32(syn_a + (io >> 5) * 128) >> (io & 31)) & 1u;
-            };
-#if BP_VARIANT == 0
-            // option check_pair: two checks per trip with their division chains interleaved (check_update_pair)
-#define BP_PAIR_LOOP(D)                                                                          \
-        if constexpr (D <= 7) {                                                                  \
-            if (p.check_pair) {                                                                  \
-                for (; i + W < end; i += 2 * W, a += 2 * W * (D * 256)) {                        \
-                    double ma_[D], mb_[D];                                                       \
-                    load_row<D>(ma_, a);                                                         \
-                    load_row<D>(mb_, a + W * (D * 256));                                         \
-                    if (fresh) { _Pragma("unroll") for (int k = 0; k < D; ++k) { ma_[k] = p0; mb_[k] = p0; } } \
-                    check_update_pair<D>(ma_, mb_, syn_of(i), syn_of(i + W));                    \
-                    store_row<D>(ma_, a);                                                        \
-                    store_row<D>(mb_, a + W * (D * 256));                                        \
-                }                                                                                \
-            }                                                                                    \
-        }
-#else
-#define BP_PAIR_LOOP(D)
-#endif
             for (int g = 0; g < p.seg.ncseg; ++g) {
                 const int deg = p.seg.cdeg[g], first = p.seg.cfirst[g], end = p.seg.cend[g], sb = p.seg.cslot[g];
 #define BP_CASE(D)                                                                               \
     {                                                                                            \
         uint32_t a = ml + (sb + (i - first) * D) * 256;                                          \
-        BP_PAIR_LOOP(D)                                                                          \
         if (p.perm_c) {                                                                          \
             for (; i < end; i += W, a += W * (D * 256)) {                                        \
                 const int io = static_cast<int>(lds_u16(corig_a + 2 * i));                       \
@@ -257,7 +233,6 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     }
                 BP_DEGREE_SWITCH(deg, BP_CASE, ;)
 #undef BP_CASE
-#undef BP_PAIR_LOOP
                 if (deg == 0 && i < end) i += ((end - i + W - 1) / W) * W;   // isolated checks: nothing to send
             }
         }

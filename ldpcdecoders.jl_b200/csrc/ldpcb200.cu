@@ -210,7 +210,6 @@ struct ldpcb200 {
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
     int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap
     int opt_grid_kernel = 1;     // small batches of codes too large for the one-CTA kernel: the grid-wide cooperative kernel
-    int opt_check_pair = 0;      // bp_smem_kernel: two checks per trip (check_update_pair)
     int opt_ring_mult = 0;       // ring slot = this many times the rows of the widest node (more nodes per loop trip of the HBM modes; 0 = auto)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
     int opt_kernel_profile = 0;  // bp_smem_kernel adds per-phase SM cycles to the handle's profile block (ldpcb200_kernel_profile)
@@ -947,7 +946,6 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
     p.tables = d.d_tables; p.tables_bytes = static_cast<int>(h->tables.size());
     p.off_colptr = h->off_colptr; p.off_ve = h->off_ve; p.off_vflip = h->off_vflip;
     p.cv_cpw = h->lean ? h->cv_cpw : 0; p.cv_stride = h->cv_stride;
-    p.check_pair = h->opt_check_pair;
     p.g_rowptr = d.d_p_rowptr; p.g_colptr = d.d_p_colptr; p.g_ve_off = d.d_ve_off; p.g_vflip = d.d_vflip;
     p.g_corig = d.d_corig; p.g_vorig = d.d_vorig;
     p.perm_c = h->perm_c; p.perm_v = h->perm_v; p.off_corig = h->off_corig; p.off_vorig = h->off_vorig;
@@ -1753,7 +1751,6 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "overlap_chunks") { h->opt_overlap_chunks = value ? 1 : 0; return 0; }
     else if (k == "grid_kernel") { h->opt_grid_kernel = value ? 1 : 0; return 0; }
-    else if (k == "check_pair") { h->opt_check_pair = value ? 1 : 0; return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "ring_mult") h->opt_ring_mult = static_cast<int>(std::min<int64_t>(std::max<int64_t>(value, 0), 4));
     else if (k == "lean") h->opt_lean = value ? 1 : 0;
