@@ -881,7 +881,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         const int smem = off_syn + 2 * h->SW * 4 + h->NW * 4;
         // ... or, when the messages of one syndrome do not fit in an SM's shared memory, the whole grid per syndrome
         // (cooperative launch, messages in L2): otherwise a lone decode! on a large code walks every edge on ONE lane
-        if (B <= limit && !h->big && smem > d.smem_optin && h->E > 0) {
+        if (B <= limit && !h->big && (smem > d.smem_optin || h->opt_grid_kernel == 2) && h->E > 0) {   // (2: always, a test hook)
             if (d.gk_blocks_per_sm < 0) {
                 int coop = 0, bps = 0;
                 cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.device);
@@ -1750,7 +1750,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
     else if (k == "overlap_chunks") { h->opt_overlap_chunks = value ? 1 : 0; return 0; }
-    else if (k == "grid_kernel") { h->opt_grid_kernel = value ? 1 : 0; return 0; }
+    else if (k == "grid_kernel") { h->opt_grid_kernel = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "ring_mult") h->opt_ring_mult = static_cast<int>(std::min<int64_t>(std::max<int64_t>(value, 0), 4));
     else if (k == "lean") h->opt_lean = value ? 1 : 0;

@@ -676,6 +676,45 @@ def test_small_batch_kernel_edge_cases(pkg, oracle, codes):
     assert_same(run_gpu(pkg, Hi, 0.05, 15, syn, want_ratio=True), ref, want_ratio=True)
 
 
+def test_grid_kernel_forced_on_small_and_irregular_graphs(pkg, oracle, codes):
+    """The grid-wide kernel forced (grid_kernel = 2) where the one-CTA kernel would normally run: configs C1-C4, semantic
+    edge cases (max_iters 1..3, prior ratio >= 1, zero syndrome, forced iterations) and a graph with empty rows / columns
+    and syndromes outside the column space, posterior ratios included -- bit for bit against the oracle."""
+    for name, per, B in (("C3", 0.05, 40), ("C2", 0.03, 33), ("C4", 0.03, 12), ("C1", 0.03, 9)):
+        H, _, mi = codes.config_matrix(name)
+        _, syn = oracle.sample(H, per, 31, 0, B)
+        ref = oracle.batch_decode(H, per, mi, syn, want_ratio=True)
+        g = run_gpu(pkg, H, per, mi, syn, want_ratio=True, grid_kernel=2, time_kernels=1)
+        assert g["persistent_launches"] == 0
+        assert_same(g, ref, want_ratio=True)
+    H, _, _ = codes.config_matrix("C3")
+    zero = np.zeros((H.shape[0], 5), dtype=np.uint8)
+    g = run_gpu(pkg, H, 0.01, 5, zero, grid_kernel=2)
+    assert not g["errors"].any() and g["converged"].all() and (g["iters"] == 1).all()
+    for per, mi in ((0.5, 7), (0.999, 4), (0.1, 1), (0.1, 2), (0.1, 3)):
+        _, syn = oracle.sample(H, 0.2, 5, 0, 48)
+        ref = oracle.batch_decode(H, per, mi, syn, want_ratio=True)
+        assert_same(run_gpu(pkg, H, per, mi, syn, want_ratio=True, grid_kernel=2), ref, want_ratio=True)
+    _, syn = oracle.sample(H, 0.05, 7, 0, 20)
+    g = run_gpu(pkg, H, 0.05, 6, syn, early_stop=0, grid_kernel=2)
+    assert (g["iters"] == 6).all()
+    rng = np.random.default_rng(19)
+    Hd = (rng.random((40, 90)) < 0.07).astype(np.uint8)
+    Hd[5, :] = 0
+    Hd[:, 11] = 0
+    for r in range(Hd.shape[0]):                             # keep every degree within the register paths (<= 12)
+        ones = np.nonzero(Hd[r])[0]
+        Hd[r, ones[12:]] = 0
+    assert Hd.sum(axis=0).max() <= 12
+    Hi = sp.csc_matrix(Hd)
+    e = (rng.random((90, 30)) < 0.05).astype(np.uint8)
+    syn = np.asarray((Hi @ e) % 2).astype(np.uint8)
+    syn[5, ::4] = 1
+    for variant in ("exact", "minsum"):
+        ref = oracle.batch_decode(Hi, 0.05, 15, syn, want_ratio=True, variant=variant)
+        assert_same(run_gpu(pkg, Hi, 0.05, 15, syn, want_ratio=True, grid_kernel=2, variant=variant), ref, want_ratio=True)
+
+
 @pytest.mark.parametrize("B", [1, 7, 64, 148])
 def test_small_batch_host_path_all_formats(pkg, oracle, codes, B):
     """Small host batches go through one staging block each way (decode_host_tiny): every boundary format,
