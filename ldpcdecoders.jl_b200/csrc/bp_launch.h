@@ -10,7 +10,8 @@ namespace bp {
 
 // Launch shapes: (threads <= 256, 2 CTAs/SM, <= 128 regs), (<= 384, 2 CTAs/SM, <= 80 regs; not for
 // the local-memory degree path), (<= 512, 1 CTA/SM, <= 128 regs; mode 0 only).
-enum KernelShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2 };
+// (<= 320, 2 CTAs/SM, <= 96 regs; HBM modes only: ten warps without the spills of the 80-register shape)
+enum KernelShape { kShape256x2 = 0, kShape384x2 = 1, kShape512x1 = 2, kShape320x2 = 3 };
 
 
 // one pair per translation unit: memory mode M, degree path B (1 = local-memory degrees), variant V

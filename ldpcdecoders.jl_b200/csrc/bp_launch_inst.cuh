@@ -26,6 +26,9 @@ cudaError_t BP_NAME(kernel_attrs_, BP_INST_MODE, BP_INST_BIG)(int shape, int sme
 #if !BP_INST_BIG
     if (shape == kShape384x2) return attrs_one<384, 2>(smem_bytes, threads, bps);
 #endif
+#if !BP_INST_BIG && BP_INST_MODE >= 1
+    if (shape == kShape320x2) return attrs_one<320, 2>(smem_bytes, threads, bps);
+#endif
 #if BP_INST_MODE == 0
     if (shape == kShape512x1) return attrs_one<512, 1>(smem_bytes, threads, bps);
 #endif
@@ -49,6 +52,9 @@ void BP_NAME(kernel_launch_, BP_INST_MODE, BP_INST_BIG)(int shape, int grid, int
     if (shape == kShape256x2) launch_one<256, 2>(grid, threads, smem_bytes, st, p);
 #if !BP_INST_BIG
     if (shape == kShape384x2) launch_one<384, 2>(grid, threads, smem_bytes, st, p);
+#endif
+#if !BP_INST_BIG && BP_INST_MODE >= 1
+    if (shape == kShape320x2) launch_one<320, 2>(grid, threads, smem_bytes, st, p);
 #endif
 #if BP_INST_MODE == 0
     if (shape == kShape512x1) launch_one<512, 1>(grid, threads, smem_bytes, st, p);

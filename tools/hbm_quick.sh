@@ -1,14 +1,14 @@
-python -m pytest tests -q -m gpu -x -k "c5 or parity_configs or staging or irregular or decision_fields or golden or minsum_large or fast32" 2>&1 | tail -2
+python -m pytest tests -q -m gpu -x -k "c5 or parity_configs or staging or irregular or decision_fields or minsum_large" 2>&1 | tail -2
 run() { python bench.py --no-cpu --no-sweep --no-e2e --steps 2 --warmup 3 "$@" 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['kernel']
 print('$*', '| value %.4g frac %.3f' % (d['value'], d['roofline']['frac']), 'warps', k['threads_per_cta']//32, 'pd', k['prefetch_distance'], 'mode', k['kernel_mode'])"; }
 run --workload C5 --batch 65536
-run --workload C5 --batch 65536 --prefetch 2
-for m in 2; do for pd in 3 2 1; do for w in 12 10 8; do run --workload C5 --batch 65536 --opt ring_mult=$m --prefetch $pd --warps $w; done; done; done
+run --workload C5 --batch 65536 --warps 10
+run --workload C5 --batch 65536 --warps 10 --prefetch 3
+run --workload C5 --batch 65536 --warps 10 --opt ring_mult=2
+run --workload C5 --batch 65536 --warps 8
 run --workload C4 --batch 1000000
-run --workload C4 --batch 1000000 --opt ring_mult=2
-run --workload C4 --batch 1000000 --opt ring_mult=2 --prefetch 2
-run --workload C4 --batch 1000000 --opt ring_mult=2 --prefetch 1
-run --workload C1 --batch 1000000 --opt ring_mult=2
+run --workload C4 --batch 1000000 --warps 10
+run --workload C4 --batch 1000000 --warps 10 --opt ring_mult=1
