@@ -79,3 +79,23 @@ def test_limits_are_reported(pkg):
     rc = lib.ldpcb200_create(1, n, colptr.ctypes.data, rowval.ctypes.data, 0, 0.1, 5, 0, None, 0, ctypes.byref(h))
     assert rc in (pkg._lib.EUNSUPPORTED, pkg._lib.ENODEVICE)
     assert lib.ldpcb200_last_error()
+
+
+def test_reference_arm_of_the_bench_emits_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU and prints one JSON line
+    with the contract's keys, the same metric / unit / config as our arm, and a cpu_baseline describing the run."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "syndromes/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "C3" in line["config"]["workload"]
