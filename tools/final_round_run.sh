@@ -12,4 +12,4 @@ print('C3', d['value'], d['e2e']['value'], r['frac'], r.get('frac_executed_21'),
 for k in ('config_C4_hgp1600_10M','config_C5_gallager100k_1M'):
     x=d[k]; print(k, x['value'], x['roofline']['frac'], x['roofline']['traffic'], x['roofline']['algorithmic_bytes_per_launch'])
 "
-bash tools/ncu_capture.sh r2 ${1:-unknown} C3 C4 C5
+bash tools/ncu_capture.sh r2 ${1:-unknown} ${FINAL_NCU:-C3 C4 C5}
