@@ -208,7 +208,8 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
-    int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap
+    int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap (2: always)
+    std::atomic<int> last_milli_iters{0};   // mean BP iterations per syndrome of the previous host batch x 1000 (0: none yet)
     int opt_grid_kernel = 1;     // small batches of codes too large for the one-CTA kernel: the grid-wide cooperative kernel
     int opt_ring_mult = 0;       // ring slot = this many times the rows of the widest node (more nodes per loop trip of the HBM modes; 0 = auto)
     int opt_pd = -1;             // cp.async prefetch distance of the HBM modes (-1: as deep as fits, 0: no staging)
@@ -1337,7 +1338,9 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
                pg_ratio = h->opt_stage_pageable && is_pageable(ratio);
     // (where the decoding kernels of consecutive chunks may overlap -- shared-memory kernel -- a chunk's tail of slow
     //  syndromes costs nothing, and six chunks measured best: C3 10 M BitMatrix 3.49e8 -> 3.65e8 syndromes/s end to end)
-    const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : ((h->lean && !ots && h->opt_overlap_chunks) ? 6 : 4));
+    const bool may_overlap = h->lean && !osd && !ots && h->opt_overlap_chunks && !pg_in && !pg_out &&
+                             (h->opt_overlap_chunks == 2 || h->last_milli_iters.load() >= 2000);
+    const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : (may_overlap ? 6 : 4));
     int64_t CH = h->opt_chunk > 0 ? h->opt_chunk
                                   : std::max<int64_t>({(Bd + nchunk_target - 1) / nchunk_target, 32768, 2 * static_cast<int64_t>(h->slots)});
     CH = std::min<int64_t>(CH, static_cast<int64_t>(budget / std::max(per_syn, 1.0)));
@@ -1428,7 +1431,12 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
         // (the shared-memory kernel keeps everything on chip and its filter list is per set: there the next chunk's kernel
         //  may start while the previous one is still finishing its slowest syndromes)
-        const bool ordered = !(h->lean && !osd && !ots && h->opt_overlap_chunks);
+        // That only pays when the call is compute-bound and the caller's buffers are pinned: a decoding kernel that starts
+        // early holds every SM until it ends, so the previous chunk's conversion kernel and copy out wait for it -- in a
+        // copy- or host-bound call (low error rate, pageable buffers) that delay is the whole call (measured: -25 % / -20 %).
+        // The handle therefore looks at the mean iteration count of its previous host batch: overlap from 2 iterations up.
+        const bool ordered = !(h->lean && !osd && !ots && h->opt_overlap_chunks && !pg_in && !pg_out &&
+                               (h->opt_overlap_chunks == 2 || h->last_milli_iters.load() >= 2000));
         if (have_prev_decode && ordered) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
         // (OSD-0 only reads the ratios of unconverged syndromes: those of iteration max_iters; a higher order post-processes
         //  every syndrome, so the ratios of each syndrome's own last iteration are needed)
@@ -1509,6 +1517,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
     CU(cudaMemcpyAsync(hc, d.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int k = 0; k < LDPCB200_NUM_COUNTERS; ++k) counters_out[k] = static_cast<int64_t>(hc[k]);
+    if (hc[0] > 0) h->last_milli_iters.store(static_cast<int>(std::min<unsigned long long>(1000ull * hc[2] / hc[0], 1000000ull)));
     if (osd && osd_stats_out) {
         unsigned long long ho[4] = {0, 0, 0, 0};
         CU(cudaMemcpyAsync(ho, d.osd_stats.p, sizeof(ho), cudaMemcpyDeviceToHost, st));
@@ -1753,7 +1762,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
-    else if (k == "overlap_chunks") { h->opt_overlap_chunks = value ? 1 : 0; return 0; }
+    else if (k == "overlap_chunks") { h->opt_overlap_chunks = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "grid_kernel") { h->opt_grid_kernel = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);
     else if (k == "ring_mult") h->opt_ring_mult = static_cast<int>(std::min<int64_t>(std::max<int64_t>(value, 0), 4));

@@ -11,8 +11,10 @@
  * This restatement is therefore pinned only by (i) line-by-line correspondence with the
  * cited reference lines, (ii) brute-force marginal KATs on cycle-free graphs,
  * (iii) an independent dense transliteration (oracle/bp_dense.py) and (iv) the
- * reference's statistical acceptance thresholds.  oracle/dump_golden.jl regenerates
- * golden vectors from the real package for anyone who has Julia.
+ * reference's statistical acceptance thresholds.  oracle/dump_golden.jl loads the text
+ * twins of the golden fixtures (tests/golden/julia_twins/) into the REAL package, runs
+ * batchdecode! for the BP and BP+OSD-0 decoders, compares bit for bit and exits non-zero
+ * on any difference: the one command that pins this file for anyone who has Julia.
  *
  * What is restated (all citations relative to /root/reference/):
  *   src/decoders/belief_propagation.jl:83-91    reset!   (scratch zeroed, priors refilled)
