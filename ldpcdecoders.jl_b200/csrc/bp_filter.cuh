@@ -33,6 +33,7 @@ struct FilterParams {
     const FilterVar *vars;
     const uint32_t *syn_words;
     uint32_t *err_words;          // rows must be zero on entry (finished lanes OR bits in)
+    int out_bits;                 // err_words is a bit stream (bit b*n + j, Julia BitMatrix) instead of rows of NW words
     uint8_t *conv;
     int32_t *iters;
     int *list, *list_count;       // work list of the syndromes that need more than one iteration
@@ -118,7 +119,16 @@ __global__ void __launch_bounds__(kFilterThreads) first_iter_filter_kernel(const
         // (D) outputs
         for (int w = 0; w < p.NW; ++w) {
             const uint32_t row = warp_transpose32(E[w * 32 + lane], lane);      // decisions 32 w .. 32 w + 31 of syndrome `lane`
-            if (((cv >> lane) & 1u) && row) p.err_words[b * p.NW + w] = row;
+            if (((cv >> lane) & 1u) && row) {
+                if (p.out_bits) {                                  // neighbouring syndromes share words: OR the two halves in
+                    const unsigned long long o = static_cast<unsigned long long>(b) * static_cast<unsigned long long>(p.n) + 32ull * w;
+                    const int lo = static_cast<int>(o & 31ull);
+                    atomicOr(p.err_words + (o >> 5), row << lo);
+                    if (lo && (row >> (32 - lo))) atomicOr(p.err_words + (o >> 5) + 1, row >> (32 - lo));
+                } else {
+                    p.err_words[b * p.NW + w] = row;
+                }
+            }
         }
         if ((cv >> lane) & 1u) {
             p.conv[b] = 1;

@@ -379,11 +379,15 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
         const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
         if (done) {
             // errors[:, sid] = guess (:227): every warp ORs the set bits it owns into the pre-zeroed packed row
-            uint32_t *row = p.err_words + static_cast<size_t>(sid) * p.NW;
+            // p.out_bits: the output is the caller's bit stream itself (Julia BitMatrix: bit sid*n + j), so that no
+            // conversion kernel stands between this kernel and the copy to the host; else packed rows of NW words
+            const unsigned long long obase = p.out_bits ? static_cast<unsigned long long>(sid) * static_cast<unsigned long long>(p.n)
+                                                        : static_cast<unsigned long long>(sid) * static_cast<unsigned long long>(p.NW) * 32ull;
             ebits_t b = ebits;
             if (cv) {                                         // the field is bits vbase .. vbase+vcnt-1 of the row
-                uint32_t *w0 = row + (vbase >> 5);
-                const int lo = vbase & 31;
+                const unsigned long long o = obase + static_cast<unsigned long long>(vbase);
+                uint32_t *w0 = p.err_words + (o >> 5);
+                const int lo = static_cast<int>(o & 31ull);
                 const unsigned long long v = static_cast<unsigned long long>(b) << lo;
                 const uint32_t v0 = static_cast<uint32_t>(v), v1 = static_cast<uint32_t>(v >> 32);
                 if (v0) atomicOr(w0, v0);
@@ -399,8 +403,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
                 if constexpr (EB64) bi = __ffsll(static_cast<long long>(b)) - 1;
                 else bi = __ffs(static_cast<int>(b)) - 1;
                 b &= b - 1;
-                const int j = vorig_at(warp + bi * W);
-                atomicOr(row + (j >> 5), 1u << (j & 31));
+                const unsigned long long o = obase + static_cast<unsigned long long>(vorig_at(warp + bi * W));
+                atomicOr(p.err_words + (o >> 5), 1u << static_cast<int>(o & 31ull));
             }
             if (warp == wO) {
                 p.conv[sid] = conv ? 1 : 0;

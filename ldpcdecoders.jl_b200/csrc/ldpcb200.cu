@@ -208,6 +208,7 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
+    int opt_direct_bits = 1;     // host batches with BitMatrix output: the shared-memory kernel writes the bit stream itself
     int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap (2: always)
     std::atomic<int> last_milli_iters{0};   // mean BP iterations per syndrome of the previous host batch x 1000 (0: none yet)
     int opt_grid_kernel = 1;     // small batches of codes too large for the one-CTA kernel: the grid-wide cooperative kernel
@@ -862,9 +863,13 @@ struct KernelTimer {
 // Decode B syndromes resident on device `d` (native packed rows); stream-ordered, one launch.
 int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_words, uint32_t *err_words,
                      uint8_t *conv, int32_t *iters, double *ratio, unsigned long long *counters, cudaStream_t st,
-                     bool ratio_last_only = false, DeviceCtx::StageSet *set = nullptr)
+                     bool ratio_last_only = false, DeviceCtx::StageSet *set = nullptr, uint32_t *err_bits = nullptr,
+                     bool *used_bits = nullptr)
 {
+    // err_bits (nullable): a buffer of ceil(B*n/32) words; when the shared-memory kernel runs, the decisions are written there
+    // as the caller's bit stream (bit b*n + j) instead of packed rows in err_words, and *used_bits is set
     DevBuf &f_list = set ? set->f_list : d.f_list, &f_count = set ? set->f_count : d.f_count;
+    if (used_bits) *used_bits = false;
     if (B <= 0) return 0;
     CU(cudaSetDevice(d.device));
     if (h->max_iters <= 0) {
@@ -970,7 +975,13 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
         p.efield_global = d.efield.as<uint32_t>();
     }
     // finished lanes OR their set decision bits into the row: rows start out zero
-    CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
+    const bool bits_out = err_bits != nullptr && h->lean;
+    if (bits_out) {
+        CU(cudaMemsetAsync(err_bits, 0, static_cast<size_t>((B * h->n + 31) / 32) * 4, st));
+        if (used_bits) *used_bits = true;
+    } else {
+        CU(cudaMemsetAsync(err_words, 0, static_cast<size_t>(B) * h->NW * 4, st));
+    }
     if (h->lean && h->opt_kernel_profile) {
         if (!d.kprof.p) {
             if ((rc = d.kprof.reserve(64))) return rc;
@@ -991,7 +1002,9 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             const int64_t Bl = std::min(kMaxLaunch, B - b0);
             bp::KernelParams q = p;
             q.B = Bl;
-            q.syn_words = syn_words + b0 * h->SW; q.err_words = err_words + b0 * h->NW; q.conv = conv + b0;
+            q.syn_words = syn_words + b0 * h->SW; q.conv = conv + b0;
+            q.err_words = bits_out ? err_bits + (b0 * h->n) / 32 : err_words + b0 * h->NW;      // (b0 is a multiple of 2^30)
+            q.out_bits = bits_out ? 1 : 0;
             q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
             if (filter) {
                 if ((rc = f_list.reserve(static_cast<size_t>(Bl) * 4)) || (rc = f_count.reserve(16))) return rc;
@@ -999,7 +1012,7 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
                 bp::FilterParams f{};
                 f.s = static_cast<int>(h->s); f.n = static_cast<int>(h->n); f.SW = h->SW; f.NW = h->NW; f.B = Bl;
                 f.vars = d.f_vars.as<bp::FilterVar>();
-                f.syn_words = q.syn_words; f.err_words = q.err_words; f.conv = q.conv; f.iters = q.iters;
+                f.syn_words = q.syn_words; f.err_words = q.err_words; f.out_bits = q.out_bits; f.conv = q.conv; f.iters = q.iters;
                 f.list = f_list.as<int>(); f.list_count = f_count.as<int>(); f.counters = counters;
                 const int fsmem = (2 * h->SW + h->NW) * 32 * 4 * bp::kFilterWarps;
                 const int fgrid = static_cast<int>(std::min<int64_t>((Bl + bp::kFilterThreads - 1) / bp::kFilterThreads, static_cast<int64_t>(d.sm_count) * 16));
@@ -1338,8 +1351,11 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
                pg_ratio = h->opt_stage_pageable && is_pageable(ratio);
     // (where the decoding kernels of consecutive chunks may overlap -- shared-memory kernel -- a chunk's tail of slow
     //  syndromes costs nothing, and six chunks measured best: C3 10 M BitMatrix 3.49e8 -> 3.65e8 syndromes/s end to end)
+    // (BitMatrix output written by the decoding kernel itself needs no conversion kernel after the decode: overlapping is
+    //  then safe in every regime; otherwise see the comment at `ordered` below)
+    const bool direct_out = err_fmt == LDPCB200_FMT_BITS && h->lean && !osd && !ots && h->opt_direct_bits;
     const bool may_overlap = h->lean && !osd && !ots && h->opt_overlap_chunks && !pg_in && !pg_out &&
-                             (h->opt_overlap_chunks == 2 || h->last_milli_iters.load() >= 2000);
+                             (h->opt_overlap_chunks == 2 || direct_out || h->last_milli_iters.load() >= 2000);
     const int nchunk_target = osd ? 2 : ((pg_in || pg_out) ? 8 : (may_overlap ? 6 : 4));
     int64_t CH = h->opt_chunk > 0 ? h->opt_chunk
                                   : std::max<int64_t>({(Bd + nchunk_target - 1) / nchunk_target, 32768, 2 * static_cast<int64_t>(h->slots)});
@@ -1428,6 +1444,15 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         } else {
             return fail(LDPCB200_EINVAL, "unsupported syndrome format %d", syn_fmt);
         }
+        // BitMatrix output: the shared-memory kernel writes the caller's bit stream itself (no conversion kernel between the
+        // decode and the copy out)
+        uint32_t *direct_bits = nullptr;
+        bool bits_done = false;
+        if (direct_out) {
+            const size_t nwb = static_cast<size_t>((Bc * n + 31) / 32);
+            if ((rc = S.raw_out.reserve(nwb * 4))) return rc;
+            direct_bits = S.raw_out.as<uint32_t>();
+        }
         // ---- decode (kernels of consecutive chunks share the per-device message store: keep them ordered)
         // (the shared-memory kernel keeps everything on chip and its filter list is per set: there the next chunk's kernel
         //  may start while the previous one is still finishing its slowest syndromes)
@@ -1435,8 +1460,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         // early holds every SM until it ends, so the previous chunk's conversion kernel and copy out wait for it -- in a
         // copy- or host-bound call (low error rate, pageable buffers) that delay is the whole call (measured: -25 % / -20 %).
         // The handle therefore looks at the mean iteration count of its previous host batch: overlap from 2 iterations up.
-        const bool ordered = !(h->lean && !osd && !ots && h->opt_overlap_chunks && !pg_in && !pg_out &&
-                               (h->opt_overlap_chunks == 2 || h->last_milli_iters.load() >= 2000));
+        const bool ordered = !may_overlap;
         if (have_prev_decode && ordered) CU(cudaStreamWaitEvent(st, d.decode_done, 0));
         // (OSD-0 only reads the ratios of unconverged syndromes: those of iteration max_iters; a higher order post-processes
         //  every syndrome, so the ratios of each syndrome's own last iteration are needed)
@@ -1445,7 +1469,7 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
         else
         rc = decode_on_device(h, d, Bc, syn_words, S.err_words.as<uint32_t>(), S.conv.as<uint8_t>(), S.iters.as<int32_t>(),
                               (ratio || (osd && h->max_iters > 0)) ? S.ratio.as<double>() : nullptr,
-                              d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0, &S);
+                              d.counters.as<unsigned long long>(), st, osd && !ratio && h->opt_osd_order == 0, &S, direct_bits, &bits_done);
         if (rc) return rc;
         CU(cudaEventRecord(d.decode_done, st));
         have_prev_decode = true;
@@ -1470,9 +1494,11 @@ int decode_host_range(ldpcb200 *h, DeviceCtx &d, int64_t b0, int64_t Bd, int64_t
             const size_t w0 = static_cast<size_t>(g0 * n / 32);
             const size_t nw = static_cast<size_t>((Bc * n + 31) / 32);
             if ((rc = S.raw_out.reserve(nw * 4))) return rc;
-            bp::unpack_bits<<<grid_for(static_cast<long long>(nw), d.sm_count), 256, 0, st>>>(
-                ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<uint32_t>(), static_cast<long long>(nw));
-            h->launches++;
+            if (!bits_done) {
+                bp::unpack_bits<<<grid_for(static_cast<long long>(nw), d.sm_count), 256, 0, st>>>(
+                    ew, static_cast<int>(n), h->NW, Bc, S.raw_out.as<uint32_t>(), static_cast<long long>(nw));
+                h->launches++;
+            }
             // (the last word of a chunk may hold bits of the next chunk's first column only when Bc*n is not a multiple
             //  of 32, i.e. in the final chunk of the batch: chunk boundaries are multiples of 32 columns)
             if ((rc = d2h(static_cast<uint32_t *>(errors) + w0, S.raw_out.p, nw * 4, pg_out))) return rc;
@@ -1762,6 +1788,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "direct_bits") { h->opt_direct_bits = value ? 1 : 0; return 0; }
     else if (k == "overlap_chunks") { h->opt_overlap_chunks = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "grid_kernel") { h->opt_grid_kernel = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "prefetch") h->opt_pd = static_cast<int>(value);

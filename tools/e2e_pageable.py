@@ -18,9 +18,9 @@ nb_out = (B * n + 63) // 64 * 8
 _, syn = oracle.sample(H, per, 3, 0, 1_000_000)
 bits = np.packbits(np.asfortranarray(syn).T.reshape(-1), bitorder="little")
 src = np.tile(bits, 10)[:nb_in].copy()
-for overlap in (1, 2, 0):
+for overlap, direct in ((1, 1), (2, 1), (0, 1), (1, 0), (2, 0), (0, 0)):
     for chunks in (0,):
-        opts = dict(overlap_chunks=overlap)
+        opts = dict(overlap_chunks=overlap, direct_bits=direct)
         if chunks:
             opts["chunk"] = (B // chunks + 31) // 32 * 32
         dec = pkg.BeliefPropagationDecoder(H, per, mi, **opts)
@@ -38,5 +38,5 @@ for overlap in (1, 2, 0):
             for _ in range(5):
                 dec.decode_raw(B, a_in, lib.FMT_BITS, 0, a_out, lib.FMT_BITS, 0, a_cv)
             dt = (time.perf_counter() - t0) / 5
-            print("per %g overlap_chunks=%d chunks=%s %-8s %.3e syndromes/s (%.2f ms per 10 M)" % (per, overlap, chunks or "auto", mem, B / dt, dt * 1e3))
+            print("per %g direct_bits=%d overlap_chunks=%d chunks=%s %-8s %.3e syndromes/s (%.2f ms per 10 M)" % (per, direct, overlap, chunks or "auto", mem, B / dt, dt * 1e3))
         dec.close()
