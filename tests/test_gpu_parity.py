@@ -244,6 +244,35 @@ def test_bit_formats_and_packed_rows(pkg, oracle, codes):
         dec.close()
 
 
+def test_direct_bit_stream_output_and_overlapping_chunks(pkg, oracle, codes):
+    """BitMatrix output written by the decoding kernel and the filter themselves (option direct_bits) with the chunk kernels
+    overlapping or ordered, on one device and split over two shards: identical to the converted output, and to the oracle.
+    n = 225 (odd) and 144: syndromes share output words with their neighbours."""
+    lib = pkg._lib
+    for name, per in (("C2", 0.02), ("C3", 0.04)):
+        H, _, mi = codes.config_matrix(name)
+        s, n = H.shape
+        B = 50_001
+        _, syn = oracle.sample(H, per, 77, 0, B)
+        bits_in = np.packbits(syn.T.reshape(-1), bitorder="little")
+        bits_in = np.concatenate([bits_in, np.zeros((-len(bits_in)) % 8, dtype=np.uint8)])
+        outs = []
+        for direct, overlap, devices in ((1, 2, [0]), (0, 0, [0]), (1, 0, [0]), (1, 2, [0, 0]), (0, 2, [0, 0])):
+            dec = pkg.BeliefPropagationDecoder(H, per, mi, devices=devices, direct_bits=direct, overlap_chunks=overlap, chunk=9984)
+            out = np.full(((B * n + 63) // 64) * 8, 0xFF, dtype=np.uint8)        # stale contents must not leak through
+            conv = np.zeros(B, dtype=np.uint8)
+            iters = np.zeros(B, dtype=np.int32)
+            dec.decode_raw(B, bits_in, lib.FMT_BITS, 0, out, lib.FMT_BITS, 0, conv, iters=iters)
+            outs.append((np.unpackbits(out, bitorder="little")[: B * n].copy(), conv.copy(), iters.copy()))
+            dec.close()
+        for o in outs[1:]:
+            assert all(np.array_equal(a, b) for a, b in zip(outs[0], o)), name
+        ref = oracle.batch_decode(H, per, mi, syn[:, :4000], nthreads=oracle.num_threads())
+        got = outs[0][0].reshape(B, n).T[:, :4000]
+        assert np.array_equal(got, ref["errors"]) and np.array_equal(outs[0][1][:4000].astype(bool), ref["converged"])
+        assert np.array_equal(outs[0][2][:4000], ref["iters"])
+
+
 def test_decode_b_single_syndrome_api(pkg, oracle, codes):
     """decode!(decoder, syndrome): aliased Float64 scratch.err, converged flag, log_probabs."""
     H, per, mi = codes.config_matrix("C1")
