@@ -105,6 +105,7 @@ struct KernelParams {
     // shared-memory carve-up (byte offsets from the dynamic smem base)
     int off_syn, off_resid, off_stage, off_nnz, off_tables, off_mbar, off_efield, off_ring;
     int off_sidq;             // bp_smem_kernel: [2][32] syndrome indices of the staged queue window
+    unsigned int *queue_ctr;  // bp_smem_kernel: null (static shares of the batch per CTA) or a zeroed counter of claimed 32-syndrome chunks
     int out_bits;             // bp_smem_kernel: err_words is a bit stream (bit sid*n + j) instead of rows of NW words
 };
 

@@ -148,8 +148,29 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_smem_kernel(const __grid_consta
     // wS moves staged syndromes into the lanes' own rows, wP prefetches the next queue window,
     // wO writes converged flags / iteration counts and keeps the counters.
     const int wS = 0, wP = (W > 1) ? 1 : 0, wO = (W > 2) ? 2 : 0;
+    // Dynamic queue (p.queue_ctr != null): instead of the static share c, c+G, ... the prefetching warp claims the next
+    // 32-syndrome chunk of the batch from a global counter whenever its sliding window reaches a new one, so CTAs whose
+    // syndromes happened to be easy keep taking work and all CTAs end together.  dq_a / dq_b: the claimed chunks that the
+    // window's two local chunks dq_k, dq_k + 1 stand for (warp wP only; the other warps read the staged indices).
+    int dq_k = -1, dq_a = 0, dq_b = 0;
+    auto claim = [&]() -> int {
+        int g = 0;
+        if (lane == 0) g = static_cast<int>(atomicAdd(p.queue_ctr, 1u));
+        return __shfl_sync(0xffffffffu, g, 0);
+    };
     auto prefetch = [&](int q_head, int buf) {            // stage[buf][w][r] <- syndrome words of entry q_head + r
-        const int sid = sid_of(q_head + lane);
+        int sid;
+        if (p.queue_ctr != nullptr) {
+            const int k0 = q_head >> 5;
+            if (dq_k < 0) { dq_a = claim(); dq_b = claim(); dq_k = 0; }
+            while (dq_k < k0) { dq_a = dq_b; dq_b = claim(); ++dq_k; }
+            const int q = q_head + lane;
+            const int g = (q >> 5) == k0 ? dq_a : dq_b;
+            const int idx = (g << 5) + (q & 31);
+            sid = (g < nchunks && idx < Bn) ? (p.list ? __ldg(p.list + idx) : idx) : -1;
+        } else {
+            sid = sid_of(q_head + lane);
+        }
         // (a refill reads the index from here instead of repeating the dependent work-list load in every warp)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(sidq_a + buf * 128 + lane * 4), "r"(sid) : "memory");
         if (sid >= 0) {

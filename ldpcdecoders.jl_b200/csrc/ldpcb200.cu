@@ -208,6 +208,7 @@ struct ldpcb200 {
     int64_t opt_small_batch = -1; // batches up to this size take the node-parallel kernel (-1: one CTA per SM, 0: never)
     int opt_osd_profile = 0;     // OSD kernel adds per-phase SM cycle counts to stats[3..7] (d_stats must then hold 8 uint64)
     int opt_ratio_last_only = 0; // ldpcb200_decode_device: write posterior ratios only in iteration max_iters (OSD pipelines)
+    int opt_dynamic_queue = 1;   // shared-memory kernel: CTAs claim 32-syndrome chunks from a global counter (0: static shares)
     int opt_direct_bits = 1;     // host batches with BitMatrix output: the shared-memory kernel writes the bit stream itself
     int opt_overlap_chunks = 1;  // host batches, shared-memory kernel: decoding kernels of consecutive chunks may overlap (2: always)
     std::atomic<int> last_milli_iters{0};   // mean BP iterations per syndrome of the previous host batch x 1000 (0: none yet)
@@ -1006,9 +1007,12 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             q.err_words = bits_out ? err_bits + (b0 * h->n) / 32 : err_words + b0 * h->NW;      // (b0 is a multiple of 2^30)
             q.out_bits = bits_out ? 1 : 0;
             q.iters = iters ? iters + b0 : nullptr; q.ratio = ratio ? ratio + b0 * h->n : nullptr;
+            // f_count: [0] length of the filter's work list, [2] chunks of the batch claimed by the CTAs (dynamic queue)
+            if ((rc = f_count.reserve(16))) return rc;
+            CU(cudaMemsetAsync(f_count.p, 0, 16, st));
+            q.queue_ctr = h->opt_dynamic_queue ? f_count.as<unsigned int>() + 2 : nullptr;
             if (filter) {
-                if ((rc = f_list.reserve(static_cast<size_t>(Bl) * 4)) || (rc = f_count.reserve(16))) return rc;
-                CU(cudaMemsetAsync(f_count.p, 0, 16, st));
+                if ((rc = f_list.reserve(static_cast<size_t>(Bl) * 4))) return rc;
                 bp::FilterParams f{};
                 f.s = static_cast<int>(h->s); f.n = static_cast<int>(h->n); f.SW = h->SW; f.NW = h->NW; f.B = Bl;
                 f.vars = d.f_vars.as<bp::FilterVar>();
@@ -1788,6 +1792,7 @@ int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value)
     }
     if (k == "family") h->opt_family = static_cast<int>(value);
     else if (k == "warps") h->opt_warps = static_cast<int>(value);
+    else if (k == "dynamic_queue") { h->opt_dynamic_queue = value ? 1 : 0; return 0; }
     else if (k == "direct_bits") { h->opt_direct_bits = value ? 1 : 0; return 0; }
     else if (k == "overlap_chunks") { h->opt_overlap_chunks = value == 2 ? 2 : (value ? 1 : 0); return 0; }
     else if (k == "grid_kernel") { h->opt_grid_kernel = value == 2 ? 2 : (value ? 1 : 0); return 0; }
