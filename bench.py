@@ -42,7 +42,7 @@ WORKLOAD_NAMES = {"C1": "Gallager (1000,10,9)", "C2": "d=15 rotated surface X ch
                   "C4": "HGP of Gallager(32,4,3) H_X", "C5": "Gallager (100002,6,3)"}
 DEFAULT_PER = {"C1": 0.01, "C2": 0.01, "C3": 0.03, "C4": 0.02, "C5": 0.02}
 DEFAULT_B = {"C1": 4096, "C2": 1_000_000, "C3": 10_000_000, "C4": 10_000_000, "C5": 1_000_000}      # BASELINE.json batch sizes
-DEFAULT_TILE = {"C4": 1_000_000, "C5": 65536}      # syndromes per launch where the batch is tiled / streamed
+DEFAULT_TILE = {"C4": 1_000_000, "C5": 262144}      # syndromes per launch where the batch is tiled / streamed
 
 
 def workload_spec(args, pkg):

@@ -420,7 +420,19 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     const long long nchunks = (p.B + 31) >> 5;
     const long long my_chunks = (c < nchunks) ? (nchunks - c + G - 1) / G : 0;
     const long long Q = my_chunks << 5;
+    // Dynamic queue (p.queue_ctr != null): warp wP claims the next chunk of the batch from a global counter whenever the
+    // sliding window reaches a new one and leaves its id in dq[k & 3] (k = local chunk number); every warp translates queue
+    // positions through that table.  Four slots: the refill of window [k0, k0+1] may still be reading while wP already
+    // writes the ids of [k0+1, k0+2] for the next one.
+    volatile int *dq = reinterpret_cast<volatile int *>(smem + p.off_mbar + 8);
+    const bool dynq = p.queue_ctr != nullptr;
+    int dq_hi = -1;                                   // highest local chunk claimed so far (warp wP only)
     auto sid_of = [&](long long q) -> long long {
+        if (dynq) {
+            const long long g = dq[(q >> 5) & 3];
+            const long long sid = (g << 5) + (q & 31);
+            return (g < nchunks && sid < p.B) ? sid : -1;
+        }
         const long long sid = (((q >> 5) * G + c) << 5) + (q & 31);
         return (q < Q && sid < p.B) ? sid : -1;
     };
@@ -431,6 +443,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp_persistent_kernel(const __grid_
     const int wS = 0, wP = (W > 1) ? 1 : 0, wO = (W > 2) ? 2 : 0;
     int sbuf = 0;                                 // stage buffer the next refill reads
     auto prefetch = [&](long long q_head, int buf) {      // stage[buf][w][r] <- syndrome words of entry q_head + r
+        if (dynq) {                                           // (warp wP) chunks of the window [q_head, q_head + 32)
+            const int k1 = static_cast<int>(q_head >> 5) + 1;
+            while (dq_hi < k1) {
+                ++dq_hi;
+                if (lane == 0) dq[dq_hi & 3] = static_cast<int>(atomicAdd(p.queue_ctr, 1u));
+            }
+            __syncwarp();
+        }
         if constexpr (kStateShared) {
             const long long sid = sid_of(q_head + lane);
             if (sid >= 0)

@@ -264,7 +264,7 @@ int smem_layout(const ldpcb200 *h, int mode, int threads, int nfw, bool efield_i
     p.off_tables = static_cast<int>(off);
     if (mode <= 1) off += static_cast<long long>(h->tables.size());
     off = (off + 7) / 8 * 8;
-    p.off_mbar = static_cast<int>(off);   off += 8;
+    p.off_mbar = static_cast<int>(off);   off += 8 + 16;              // mbarrier + the dynamic queue's four claimed chunk ids
     off = (off + 127) / 128 * 128;
     // cp.async ring (modes 1/2): per warp pd+1 slots of one node's rows (max register degree)
     const int maxdeg = std::min(std::max(h->max_cdeg, h->max_vdeg), bp::kMaxRegDegree);
@@ -1041,6 +1041,11 @@ int decode_on_device(ldpcb200 *h, DeviceCtx &d, int64_t B, const uint32_t *syn_w
             h->launches++;
         }
     } else {
+        if (h->opt_dynamic_queue) {                       // CTAs claim 32-syndrome chunks from a zeroed counter
+            if ((rc = f_count.reserve(16))) return rc;
+            CU(cudaMemsetAsync(f_count.p, 0, 16, st));
+            p.queue_ctr = f_count.as<unsigned int>() + 2;
+        }
         KernelTimer timer(h, d, st);
         kernel_launch_dispatch(h->variant, h->mode, h->big, h->shape, grid, thr, h->smem_bytes, st, p);
         h->launches++;
