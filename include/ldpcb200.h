@@ -130,6 +130,8 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   "overlap_chunks" (host batches on the shared-memory kernel: decoding kernels of consecutive chunks may overlap; 1, default:
  *   with pinned buffers and BitMatrix output, or once the previous batch averaged >= 2 iterations per syndrome; 0 never;
  *   2 always), "direct_bits" (1, default: with BitMatrix output the shared-memory kernel writes the caller's bit stream itself),
+ *   "dynamic_queue" (1, default: the CTAs of the persistent kernels claim 32-syndrome chunks of the batch from a global
+ *   counter; 0 = static shares c, c+G, ...),
  *   "stage_pageable" (1, default: pageable host buffers are staged through pinned blocks), "nccl" (1, default: a
  *   multi-device handle sums its counters with ncclAllReduce), "time_kernels" (see ldpcb200_kernel_time),
  *   "kernel_profile" (see ldpcb200_kernel_profile), "osd_profile"; experiments that measured no gain and stay off:
