@@ -19,7 +19,7 @@ for w in $WHAT; do
     C3)  cap c3 bp_smem C3 exact 2 10000000 $COMMON ;;
     C3MS) cap c3_minsum bp_smem C3 minsum 2 10000000 $COMMON --variant minsum ;;
     C4)  cap c4 bp_persistent C4 exact 1 1000000 $COMMON --workload C4 --batch 1000000 ;;
-    C5)  cap c5 bp_persistent C5 exact 1 262144 $COMMON --workload C5 --batch 262144 ;;
+    C5)  cap c5 bp_persistent C5 exact 1 65536 $COMMON --workload C5 --batch 65536 ;;   # (a 262144-syndrome launch takes ncu more than ten minutes to replay)
     C2)  cap c2 bp_smem C2 exact 2 1000000 $COMMON --workload C2 ;;
   esac
 done
