@@ -135,7 +135,9 @@ int ldpcb200_info(const ldpcb200_t *h, ldpcb200_info_t *out);
  *   "stage_pageable" (1, default: pageable host buffers are staged through pinned blocks), "nccl" (1, default: a
  *   multi-device handle sums its counters with ncclAllReduce), "time_kernels" (see ldpcb200_kernel_time),
  *   "kernel_profile" (see ldpcb200_kernel_profile), "osd_profile"; experiments that measured no gain and stay off:
- *   "dual" (two teams per CTA), "max_ctas_per_sm". */
+ *   "dual" (two teams per CTA), "max_ctas_per_sm";
+ *   "contiguous_variables" (1, default: the shared-memory kernel gives every warp a contiguous block of variables where the
+ *   code has a uniform variable degree; 0 = round-robin ownership). */
 int ldpcb200_set_option(ldpcb200_t *h, const char *key, int64_t value);
 
 /* Replaces batchdecode!(decoder, syndromes, errors, success)

@@ -99,3 +99,21 @@ def test_reference_arm_of_the_bench_emits_the_contract_keys():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "C3" in line["config"]["workload"]
+
+
+def test_documented_options_exist_in_the_library_source():
+    """Every option name the header documents for ldpcb200_set_option is handled by the library, and every option the
+    library handles is documented (guards the header against drifting from csrc/ldpcb200.cu)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ldpcb200.h")).read()
+    src = open(os.path.join(root, "ldpcdecoders.jl_b200", "csrc", "ldpcb200.cu")).read()
+    a = hdr.index("Tunables, set before the first decode")
+    b = hdr.index("int ldpcb200_set_option")
+    documented = set(re.findall(r'"([a-z_0-9]+)"', hdr[a:b]))
+    body = src[src.index("int ldpcb200_set_option("):]
+    body = body[:body.index("\nint ldpcb200_info(")]
+    handled = set(re.findall(r'k == "([a-z_0-9]+)"', body))
+    assert handled, "option parser not found"
+    assert documented - handled == set(), "documented but not handled: %s" % sorted(documented - handled)
+    undocumented = handled - documented - {"slots"}            # ("slots": accepted for compatibility, unused)
+    assert undocumented == set(), "handled but not documented in the header: %s" % sorted(undocumented)
